@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Learner steps/sec on synthetic (T=20, B=4096, O=24, A=4, H=256) trajectories.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm (default): one process per GPU (torchrun for N > 1), global batch B=4096 sharded
+B/N per rank ("scaling": "strong"), one NCCL all-reduce of [gradient | loss scalars] per step.
+  value  : learner steps/s with the batch already resident in HBM; each of the K timed steps
+           is bracketed by CUDA events on the launching stream, L2 flushed between steps
+  e2e    : the same through the host-facing API - every step copies that step's inputs from
+           pinned host memory (one DMA), runs the update and reads the loss scalars back
+  roofline / kernels : per-kernel CUDA-event timings of the same launch sequence (eager, L2
+           flushed) against the binding roof of each kernel (HBM for V-trace/loss/optimizer,
+           FP32 FMA pipe for the MLP kernels - see DESIGN.md)
+  cpu_baseline : the per-trajectory float64 torch port of learner.py (oracle/) on host cores
+Reference arm (--impl reference): rank 0 times that CPU port alone and prints its own line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(T=20, B=4096, O=24, A=4, H=256)
+WORKLOAD_NAME = "c4: synthetic obs=24 act=4 hidden=256, T=20 B=4096 (BASELINE.json configs[3])"
+METRIC = "learner steps/sec on synthetic (T=20,B=4096) trajectories"
+SMS, FP32_LANES = 148, 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+def hparams(B):
+    from torched_impala_b200.utils import default_hparams
+
+    return default_hparams(batch_size=B, max_timesteps=WORKLOAD["T"], policy_hidden_dims=WORKLOAD["H"],
+                           value_fn_hidden_dims=WORKLOAD["H"])
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def time_cpu_port(sample_B: int, warm: int, timed: int, threads: int):
+    """Per-trajectory float64 port of learner.py:75-183 on `threads` host threads."""
+    import torch
+
+    from oracle.cpu_learner_port import CpuLearnerPort
+    from torched_impala_b200 import synth
+
+    w = WORKLOAD
+    hp = hparams(sample_B)
+    port = CpuLearnerPort(synth.init_params(0, w["O"], w["A"], w["H"]), hp, threads=threads)
+    trajs = synth.to_trajectories(synth.make_batch(1, w["T"], sample_B, w["O"], w["A"]))
+    times = []
+    for i in range(warm + timed):
+        t0 = time.perf_counter()
+        port.update(trajs)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    return statistics.median(times)
+
+
+def cpu_baseline(sample_B=512, warm=1, timed=3):
+    cores = os.cpu_count() or 1
+    t1 = time_cpu_port(sample_B, warm, timed, 1)
+    tn = time_cpu_port(sample_B, warm, timed, cores) if cores > 1 else t1
+    best_t, best_c = (t1, 1) if t1 <= tn else (tn, cores)
+    scale = WORKLOAD["B"] / sample_B  # cost is linear in B (python loop over trajectories)
+    return dict(value=1.0 / (best_t * scale), unit="steps/s", cores=best_c, kind="port",
+                sample=(f"oracle/cpu_learner_port.py, {warm}+{timed} updates of B={sample_B} "
+                        f"(T=20,O=24,H=256), median, scaled x{scale:g} to B=4096 (cost linear in B); "
+                        f"1 thread {t1 * 1e3:.0f} ms, {cores} threads {tn * 1e3:.0f} ms per B={sample_B} update"),
+                host_cores=cores)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb = cpu_baseline(sample_B=512, warm=warm, timed=steps)
+    line = dict(metric=METRIC, value=cb["value"], unit="steps/s", n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD_NAME, **WORKLOAD, global_batch=WORKLOAD["B"]),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# -------------------------------------------------------------------------------- own arm
+def kernel_breakdown(eng, flush, iters=20):
+    """CUDA-event time of every C-ABI launch of one step, eager, L2 flushed before each."""
+    import ctypes as C
+
+    import torch
+
+    from torched_impala_b200 import _cabi
+    from torched_impala_b200.engine import _ptr
+
+    lib, hp, w = eng.lib, eng.hp, WORKLOAD
+    T, B, O, A = eng.T, eng.B, eng.O, eng.A
+    st = C.c_void_p(eng.stream.cuda_stream)
+    p_pi = C.c_void_p(eng.params.data_ptr())
+    p_vf = C.c_void_p(eng.params.data_ptr() + 4 * eng.n_pi)
+    g_pi = C.c_void_p(eng.comm.data_ptr())
+    g_vf = C.c_void_p(eng.comm.data_ptr() + 8 * eng.n_pi)
+    scal = C.c_void_p(eng.comm.data_ptr() + 8 * eng.n_total)
+    obs = _ptr(eng.d["obs"])
+    calls = {
+        "mlp_forward(policy)": lambda: lib.impala_mlp_forward(obs, p_pi, _ptr(eng.logits), eng.M_pi, O, eng.H_pi, A, st),
+        "mlp_forward(value_fn)": lambda: lib.impala_mlp_forward(obs, p_vf, _ptr(eng.values), eng.M_vf, O, eng.H_v, 1, st),
+        "vtrace_loss": lambda: lib.impala_vtrace_loss(
+            _ptr(eng.logits), _ptr(eng.d["beh_logits"]), _ptr(eng.d["actions"]), _ptr(eng.d["rewards"]),
+            _ptr(eng.d["done"]), _ptr(eng.d["lens"]), _ptr(eng.values), _ptr(eng.vs), _ptr(eng.pg_adv),
+            _ptr(eng.dlogits), _ptr(eng.dv), scal, T, B, A, float(hp.gamma), float(hp.rho_bar),
+            float(hp.c_bar), float(hp.v_loss_c), float(hp.policy_loss_c), float(hp.entropy_c),
+            float(eng.inv_batch), eng.mode, st),
+        "mlp_backward(policy)": lambda: lib.impala_mlp_backward(obs, p_pi, _ptr(eng.dlogits), g_pi, _ptr(eng.ws_pi), eng.ws_pi_bytes, eng.M_pi, O, eng.H_pi, A, st),
+        "mlp_backward(value_fn)": lambda: lib.impala_mlp_backward(obs, p_vf, _ptr(eng.dv), g_vf, _ptr(eng.ws_vf), eng.ws_vf_bytes, eng.M_vf, O, eng.H_v, 1, st),
+    }
+    H = eng.H_pi
+    P = 2 * O * H + 3 * H + H * A + A + 1
+    fl = {  # algorithmic FLOPs (no recompute counted)
+        "mlp_forward(policy)": 2.0 * eng.M_pi * (O * H + H * A),
+        "mlp_forward(value_fn)": 2.0 * eng.M_vf * (O * eng.H_v + eng.H_v),
+        "mlp_backward(policy)": 2.0 * eng.M_pi * (O * H + 2 * H * A),
+        "mlp_backward(value_fn)": 2.0 * eng.M_vf * (O * eng.H_v + 2 * eng.H_v),
+    }
+    by = {  # algorithmic bytes of the HBM-bound kernels
+        # in: cur+beh logits, actions, rewards, done, v ; out: vs, pg_adv, dlogits, dv
+        "vtrace_loss": 4.0 * T * B * (2 * A + 2) + T * B + 4.0 * (T + 1) * B
+                       + 4.0 * (T + 1) * B + 4.0 * T * B + 4.0 * T * B * A + 4.0 * (T + 1) * B,
+    }
+    out = {}
+    with torch.cuda.stream(eng.stream):
+        for name, fn in calls.items():
+            ts = []
+            for _ in range(iters):
+                flush()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(eng.stream)
+                _cabi.check(fn(), name)
+                e1.record(eng.stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            out[name] = dict(us=statistics.median(ts), flops=fl.get(name), bytes=by.get(name))
+        # optimizer: needs a valid gradient in comm; time it on copies so parameters stay intact
+        ts = []
+        keep = [t.clone() for t in (eng.params, eng.adam_m, eng.adam_v, eng.adam_step)]
+        for _ in range(iters):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(eng.stream)
+            eng._enqueue_opt()
+            e1.record(eng.stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        for dst, src in zip((eng.params, eng.adam_m, eng.adam_v, eng.adam_step), keep):
+            dst.copy_(src)
+        # read grad f64 + params/m/v read+write f32
+        out["clip_adam"] = dict(us=statistics.median(ts), flops=None, bytes=(8.0 + 6 * 4.0) * eng.n_total)
+    eng.synchronize()
+    return out
+
+
+def run_own_arm(args):
+    import torch
+
+    from torched_impala_b200 import synth
+    from torched_impala_b200.engine import LearnerEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the learner has no CPU path)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun")
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    w = WORKLOAD
+    Bl = w["B"] // world
+    hp = hparams(w["B"])
+    eng = LearnerEngine(w["T"], Bl, w["O"], w["A"], w["H"], w["H"], hp, global_batch=w["B"],
+                        device=f"cuda:{local}", process_group=pg, use_graph=not args.no_graph)
+    eng.load_state(synth.init_params(0, w["O"], w["A"], w["H"]))
+    batches = [synth.shard_batch(synth.make_batch(1 + i, w["T"], w["B"], w["O"], w["A"]), rank, world)
+               for i in range(2)]
+    for i, b in enumerate(batches):
+        eng.fill_host(b, i)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)  # 2x the 126 MB L2
+
+    def flush():
+        flush_buf.zero_()  # on the current (= engine) stream
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        import torch.distributed as dist
+
+        t = torch.tensor([x], dtype=torch.float64, device=eng.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident ("value") ----------------
+    eng.ingest(0)
+    eng.synchronize()
+    with torch.cuda.stream(eng.stream):
+        for _ in range(max(3, args.warmup)):
+            flush()
+            eng.step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = []
+    with torch.cuda.stream(eng.stream):
+        for _ in range(args.steps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(eng.stream)
+            eng.step()
+            e1.record(eng.stream)
+            evs.append((e0, e1))
+    barrier()
+    dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    launches = eng.launches_per_step * args.steps
+    scal_dev = eng.read_scalars()
+
+    # ---------------- end to end through host buffers ----------------
+    for i in range(max(3, args.warmup)):
+        eng.ingest(i % 2)
+        eng.step()
+        eng.read_scalars()
+    barrier()
+    t0 = time.perf_counter()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(eng.stream)
+    for i in range(args.steps):
+        eng.ingest(i % 2)        # H2D of this step's inputs from pinned memory
+        eng.step()
+        last = eng.read_scalars()  # D2H of the step's loss scalars (synchronises)
+    e_stop.record(eng.stream)
+    barrier()
+    e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_dev_ms = max_over_ranks(e_start.elapsed_time(e_stop))
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- per-kernel roofline (rank 0 reports) ----------------
+    with torch.cuda.stream(eng.stream):
+        kern = kernel_breakdown(eng, flush)
+    pk = peaks()
+    fp32_peak = SMS * FP32_LANES * 2 * pk["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at max SM clock
+    kernels = {}
+    for name, k in kern.items():
+        ent = dict(us=round(k["us"], 3))
+        if k["flops"]:
+            ach = k["flops"] / (k["us"] * 1e-6) / 1e12
+            ent.update(bound="fp32", achieved=round(ach, 3), peak=round(fp32_peak, 2), unit="TFLOP/s",
+                       frac=round(ach / fp32_peak, 4))
+        else:
+            ach = k["bytes"] / (k["us"] * 1e-6) / 1e9
+            ent.update(bound="hbm", achieved=round(ach, 1), peak=pk["hbm_gbs"], unit="GB/s",
+                       frac=round(ach / pk["hbm_gbs"], 4))
+        kernels[name] = ent
+    dom = max(kernels, key=lambda n: kernels[n]["us"])
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get(dom)
+    roofline = dict(kernel=dom, traffic=traffic,
+                    peak_source=(pk["source"] if kernels[dom]["bound"] == "hbm" else
+                                 f"148 SMs x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (max SM clock, "
+                                 f"{pk['source']}); MEASURED_PEAKS has no FP32 figure"),
+                    **{k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")})
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
+    cb = cpu_baseline() if world == 1 and not args.no_cpu else None
+    ms = dev_ms / args.steps
+    line = dict(
+        metric=METRIC, value=1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps,
+        warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True, scaling="strong",
+        vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=WORKLOAD_NAME, **w, global_batch=w["B"], per_gpu_batch=Bl,
+                    parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step)"
+                    if world > 1 else "single GPU",
+                    l2="flushed between timed steps (256 MiB memset on the launching stream)",
+                    cuda_graph=not args.no_graph, timing="sum of per-step CUDA-event intervals, max over ranks"),
+        clocks=clocks, gpu_launches=launches,
+        e2e=dict(value=args.steps / (e2e_wall_ms * 1e-3), unit="steps/s",
+                 h2d_bytes_per_step=int(eng.slab_bytes) * world, d2h_bytes_per_step=48 * world,
+                 ms_per_step_wall=e2e_wall_ms / args.steps, ms_per_step_device=e2e_dev_ms / args.steps,
+                 note="wall clock around K x (H2D from pinned slab, step, D2H of scalars), max over ranks"),
+        roofline=roofline, kernels=kernels,
+        loss=dict(device_resident=scal_dev["total_loss"], e2e_last=last["total_loss"]),
+    )
+    if cb:
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graphs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+/*
+ * impala_b200.h - C ABI of the B200-native IMPALA learner hot path.
+ *
+ * Every entry point replaces a stretch of the reference learner's update
+ * (threewisemonkeys-as/torched_impala, learner.py) that the reference executes as
+ * per-trajectory ATen calls on the CPU.  The reference has no FFI of its own (it
+ * is pure Python); these are the functions its `Learner._learn` would bind through
+ * ctypes (see INTEGRATION.md for the stub).  Conventions:
+ *
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *     parameter name starts with `host_`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing allocates, frees or synchronises; every call only enqueues work and
+ *     is CUDA-graph capturable; the caller owns all buffers;
+ *   - return value: 0 = ok, >0 = cudaError_t of the failed launch,
+ *     <0 = IMPALA_ERR_* (argument / unsupported-shape errors).  No exceptions.
+ *
+ * Batch layout in HBM (time-major, dense, zero padded; `lens[b]` valid steps):
+ *   obs (T+1,B,O) f32 | beh_logits (T,B,A) f32 | actions (T,B) i32 |
+ *   rewards (T,B) f32 | done (T,B) u8 | lens (B) i32
+ * Parameter block of one MLP (Linear(O,H) -> ReLU -> Linear(H,N2)), f32, every
+ * tensor starting on a 32-float boundary:  W1 (H,O) | b1 (H) | W2 (N2,H) | b2 (N2)
+ * (row-major = torch nn.Linear.weight layout, reference models.py:13-18,41-46).
+ */
+#ifndef IMPALA_B200_H
+#define IMPALA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPALA_OK 0
+#define IMPALA_ERR_BAD_ARG (-1)
+#define IMPALA_ERR_UNSUPPORTED_SHAPE (-2)
+#define IMPALA_ERR_WORKSPACE_TOO_SMALL (-3)
+
+#define IMPALA_MODE_REFERENCE 0 /* learner.py:126,130 as written (v[:1], double v[i+1] subtraction) */
+#define IMPALA_MODE_PAPER 1     /* Espeholt et al. 2018 recurrence; not parity-checked */
+
+#define IMPALA_PARAM_ALIGN 32 /* floats */
+
+/* Version / build info: returns the sm arch the library was compiled for (100). */
+int impala_abi_version(void);
+int impala_compiled_sm(void);
+
+/* Parameter-block layout of one MLP.  offsets[4] = float offsets of W1,b1,W2,b2;
+ * *total = padded float count of the block (multiple of IMPALA_PARAM_ALIGN). */
+int impala_param_layout(int O, int H, int N2, int64_t offsets[4], int64_t* total);
+
+/* Byte offsets of the six batch tensors inside one contiguous slab (each 256-byte
+ * aligned) and the slab size; the same layout is used for the pinned host slab and
+ * the device slab so that ingest is ONE cudaMemcpyAsync.
+ * order: obs, beh_logits, actions, rewards, done, lens.
+ * Replaces the five torch.stack calls at learner.py:104-109,117. */
+int impala_batch_layout(int T, int B, int O, int A, int64_t offsets[6], int64_t* total_bytes);
+
+/* Host slab -> device slab, async on `stream` (host memory should be pinned). */
+int impala_ingest(void* dev_slab, const void* host_slab, int64_t bytes, void* stream);
+
+/* out[m, :] = relu(x[m, :] W1^T + b1) W2^T + b2 for m < M.
+ * Replaces MlpPolicy.forward / MlpValueFn.forward in eval mode
+ * (models.py:23-25, :51-52) as called at learner.py:112-113 on the flattened
+ * (T*B, O) / ((T+1)*B, O) batch.  x row-major (M,O); out row-major (M,N2). */
+int impala_mlp_forward(const float* x, const float* params, float* out, int M, int O, int H,
+                       int N2, void* stream);
+
+/* Bytes of scratch impala_mlp_backward needs for these dimensions. */
+int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2);
+
+/* Gradient of sum_m <dout[m,:], mlp(x[m,:])> w.r.t. the parameter block, written
+ * (not accumulated) as float64 into grad[0 .. total) in parameter-block layout
+ * (pad entries = 0).  Hidden activations are recomputed from x, nothing is saved
+ * by the forward.  Replaces the MLP part of loss.backward() at learner.py:175. */
+int impala_mlp_backward(const float* x, const float* params, const float* dout, double* grad,
+                        void* workspace, int64_t workspace_bytes, int M, int O, int H, int N2,
+                        void* stream);
+
+/* V-trace only (learner.py:116-135): from current/behaviour logits, actions,
+ * rewards, done, lens and the value estimates v (T+1,B) produce
+ * vs (T+1,B) [the reference's `vt` after :131] and pg_adv (T,B).
+ * Padded positions are written as 0. */
+int impala_vtrace(const float* cur_logits, const float* beh_logits, const int32_t* actions,
+                  const float* rewards, const uint8_t* done, const int32_t* lens, const float* v,
+                  float* vs, float* pg_adv, int T, int B, int A, float gamma, float rho_bar,
+                  float c_bar, int mode, void* stream);
+
+/* V-trace + the three losses + their closed-form backward in one kernel
+ * (learner.py:116-162 and the non-MLP part of :175; helper functions :298-321).
+ *   dlogits (T,B,A), dv (T+1,B): d total_loss / d logits, d total_loss / d v
+ *   scalars[0..4) (float64, zeroed by this call, then atomically accumulated):
+ *     value_fn_loss, policy_loss, policy_entropy (each sum_b(..)*inv_batch as logged at
+ *     learner.py:160-162) and batch_mean_reward (:108).
+ *   vs / pg_adv may be NULL when the caller does not need them.
+ *   inv_batch = 1 / GLOBAL batch size (all ranks), so shard results add up. */
+int impala_vtrace_loss(const float* cur_logits, const float* beh_logits, const int32_t* actions,
+                       const float* rewards, const uint8_t* done, const int32_t* lens,
+                       const float* v, float* vs, float* pg_adv, float* dlogits, float* dv,
+                       double* scalars, int T, int B, int A, float gamma, float rho_bar,
+                       float c_bar, float v_loss_c, float policy_loss_c, float entropy_c,
+                       float inv_batch, int mode, void* stream);
+
+/* Per-group gradient clipping + Adam in one launch (learner.py:176-183).
+ *   params/m/v: f32 [n_total]; grad: f64 [n_total] (the possibly all-reduced sum);
+ *   group 0 = [0, n_policy) (policy net), group 1 = [n_policy, n_total) (value net);
+ *   each group is scaled by min(1, max_norm / (||g||_2 + 1e-6)) as
+ *   torch.nn.utils.clip_grad_norm_ does, then one Adam step (no weight decay) with
+ *   bias correction from the device-side counter *step (incremented by the kernel).
+ *   norms_out (f64[2], may be NULL) receives the two pre-clip norms. */
+int impala_clip_adam(float* params, const double* grad, float* m, float* v, int64_t* step,
+                     int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
+                     float beta2, float eps, double* norms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPALA_B200_H */

@@ -1,0 +1,42 @@
+// Layout helpers and ingest: the parts of the C ABI that launch no kernel of their own.
+#include "common.cuh"
+
+extern "C" int impala_abi_version(void) { return 1; }
+
+extern "C" int impala_compiled_sm(void) { return 100; }
+
+extern "C" int impala_param_layout(int O, int H, int N2, int64_t offsets[4], int64_t* total) {
+    if (O < 1 || H < 1 || N2 < 1 || !offsets || !total) return IMPALA_ERR_BAD_ARG;
+    const MlpLayout l = impala_make_layout(O, H, N2);
+    offsets[0] = l.oW1, offsets[1] = l.ob1, offsets[2] = l.oW2, offsets[3] = l.ob2;
+    *total = l.total;
+    return IMPALA_OK;
+}
+
+extern "C" int impala_batch_layout(int T, int B, int O, int A, int64_t offsets[6],
+                                   int64_t* total_bytes) {
+    if (T < 1 || B < 1 || O < 1 || A < 1 || !offsets || !total_bytes) return IMPALA_ERR_BAD_ARG;
+    const int64_t al = 256;
+    int64_t off = 0;
+    const int64_t sizes[6] = {
+        (int64_t)(T + 1) * B * O * 4,  // obs        f32
+        (int64_t)T * B * A * 4,        // beh_logits f32
+        (int64_t)T * B * 4,            // actions    i32
+        (int64_t)T * B * 4,            // rewards    f32
+        (int64_t)T * B,                // done       u8
+        (int64_t)B * 4,                // lens       i32
+    };
+    for (int i = 0; i < 6; ++i) {
+        offsets[i] = off;
+        off = impala_round_up(off + sizes[i], al);
+    }
+    *total_bytes = off;
+    return IMPALA_OK;
+}
+
+extern "C" int impala_ingest(void* dev_slab, const void* host_slab, int64_t bytes, void* stream) {
+    if (!dev_slab || !host_slab || bytes < 0) return IMPALA_ERR_BAD_ARG;
+    cudaError_t e = cudaMemcpyAsync(dev_slab, host_slab, (size_t)bytes, cudaMemcpyHostToDevice,
+                                    (cudaStream_t)stream);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}

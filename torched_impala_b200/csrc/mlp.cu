@@ -1,0 +1,161 @@
+// Two-layer MLP forward / backward on FP32 CUDA cores (reference models.py:12-25,40-52
+// in eval mode; autograd of the same at learner.py:175).
+//
+// Mapping ("a thread owns hidden units"): thread `tid` owns hidden units
+// j = tid + q*blockDim (q < JPT) and keeps their W1 rows, b1 and W2 columns in registers
+// for the lifetime of its persistent CTA.  A tile is 32 consecutive rows of the flattened
+// (M, O) observation matrix, staged in shared memory and consumed in register blocks of 8
+// rows through warp-broadcast 128-bit loads (8*JPT FFMA per LDS.128).  Hidden activations
+// never leave registers: the forward reduces layer 2 across the CTA with a transposing
+// warp butterfly (the CTA spans the whole hidden layer); the backward recomputes them,
+// and because every gradient entry of W1/b1/W2 belongs to exactly one hidden unit each
+// thread accumulates its own slice in registers across all its tiles - no atomics,
+// deterministic; wide hidden layers are split over blockIdx.y.  Per-CTA partials are then
+// summed in float64 by a second small kernel.
+//
+// This file: host-side configuration, occupancy cache, the partial reduction and the
+// C-ABI entry points.  Kernel templates: mlp_kernels.cuh; instantiations: mlp_inst.cu.
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "mlp_kernels.cuh"
+
+namespace {
+
+struct GridInfo {
+    int ctas_per_sm, sms;
+};
+std::mutex g_cfg_mutex;
+std::map<std::tuple<const void*, int, int, size_t>, GridInfo> g_cfg_cache;
+
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, double* __restrict__ grad,
+                                       int nparts, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += (double)ws[(size_t)c * total + i];
+    grad[i] = s;
+}
+
+bool pick_config(int O, int H, int N2, bool bwd, MlpConfig* c) {
+    if (O < 1 || H < 1 || N2 < 1) return false;
+    if (O <= 8) c->op = 8;
+    else if (O <= 24) c->op = 24;
+    else if (O <= 32) c->op = 32;
+    else if (O <= 64) c->op = 64;
+    else return false;
+    if (N2 <= 1) c->np = 1;
+    else if (N2 <= 4) c->np = 4;
+    else if (N2 <= 16) c->np = 16;
+    else return false;
+    // register budget: forward holds JPT*OP weights, backward 2*JPT*OP (weights + gradient)
+    if (H < 128 || (bwd && c->op == 64)) c->jpt = 1, c->maxt = bwd && H >= 128 ? 256 : 128;
+    else c->jpt = 2, c->maxt = 256;
+    const int want = (int)impala_round_up((H + c->jpt - 1) / c->jpt, 32);
+    if (bwd) {
+        c->threads = want < c->maxt ? want : c->maxt;
+        c->slices = (H + c->threads * c->jpt - 1) / (c->threads * c->jpt);
+    } else {
+        if (want > c->maxt) return false;  // forward needs the whole hidden layer in one CTA
+        c->threads = want;
+        c->slices = 1;
+    }
+    return true;
+}
+
+bool fill_args(MlpArgs* a, MlpConfig* c, size_t* smem, bool bwd, int M, int O, int H, int N2) {
+    if (M < 1 || !pick_config(O, H, N2, bwd, c)) return false;
+    a->M = M, a->O = O, a->H = H, a->N2 = N2;
+    a->num_tiles = (M + kRows - 1) / kRows;
+    a->lay = impala_make_layout(O, H, N2);
+    const size_t tail = bwd ? (size_t)kRows * c->np : (size_t)(c->threads / 32) * kRows * c->np;
+    *smem = ((size_t)kRows * c->op + tail) * sizeof(float);
+    return true;
+}
+
+int dispatch(bool bwd, const MlpArgs& a, const MlpConfig& c, size_t smem, cudaStream_t st,
+             int* grid) {
+    switch (c.op) {
+        case 8: return bwd ? impala_mlp_bwd_op8(a, c, smem, st, grid) : impala_mlp_fwd_op8(a, c, smem, st, grid);
+        case 24: return bwd ? impala_mlp_bwd_op24(a, c, smem, st, grid) : impala_mlp_fwd_op24(a, c, smem, st, grid);
+        case 32: return bwd ? impala_mlp_bwd_op32(a, c, smem, st, grid) : impala_mlp_fwd_op32(a, c, smem, st, grid);
+        default: return bwd ? impala_mlp_bwd_op64(a, c, smem, st, grid) : impala_mlp_fwd_op64(a, c, smem, st, grid);
+    }
+}
+
+}  // namespace
+
+// Persistent grid = resident CTAs per SM x SM count, computed once per
+// (kernel, device, block size, shared memory) and cached.
+int impala_mlp_launch(void (*kernel)(MlpArgs), const MlpArgs& a, const MlpConfig& c, size_t smem,
+                      cudaStream_t st, int* grid_out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    GridInfo gi;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        const auto key = std::make_tuple((const void*)kernel, dev, c.threads, smem);
+        auto it = g_cfg_cache.find(key);
+        if (it == g_cfg_cache.end()) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gi.ctas_per_sm, kernel, c.threads, smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaDeviceGetAttribute(&gi.sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return (int)e;
+            if (gi.ctas_per_sm < 1) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+            g_cfg_cache[key] = gi;
+        } else {
+            gi = it->second;
+        }
+    }
+    int grid = gi.ctas_per_sm * gi.sms / c.slices;
+    if (grid < 1) grid = 1;
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    if (grid > kMaxParts) grid = kMaxParts;
+    kernel<<<dim3(grid, c.slices), c.threads, smem, st>>>(a);
+    *grid_out = grid;
+    return impala_launch_status();
+}
+
+extern "C" int impala_mlp_forward(const float* x, const float* params, float* out, int M, int O,
+                                  int H, int N2, void* stream) {
+    if (!x || !params || !out) return IMPALA_ERR_BAD_ARG;
+    MlpArgs a{};
+    MlpConfig c{};
+    size_t smem;
+    if (!fill_args(&a, &c, &smem, false, M, O, H, N2)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+    a.x = x, a.params = params, a.out = out;
+    int grid = 0;
+    return dispatch(false, a, c, smem, (cudaStream_t)stream, &grid);
+}
+
+extern "C" int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2) {
+    MlpConfig c{};
+    if (M < 1 || !pick_config(O, H, N2, true, &c)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+    int64_t tiles = (M + kRows - 1) / kRows;
+    if (tiles > kMaxParts) tiles = kMaxParts;
+    return tiles * impala_make_layout(O, H, N2).total * (int64_t)sizeof(float);
+}
+
+extern "C" int impala_mlp_backward(const float* x, const float* params, const float* dout,
+                                   double* grad, void* workspace, int64_t workspace_bytes, int M,
+                                   int O, int H, int N2, void* stream) {
+    if (!x || !params || !dout || !grad || !workspace) return IMPALA_ERR_BAD_ARG;
+    MlpArgs a{};
+    MlpConfig c{};
+    size_t smem;
+    if (!fill_args(&a, &c, &smem, true, M, O, H, N2)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+    if (workspace_bytes < impala_mlp_backward_workspace(M, O, H, N2))
+        return IMPALA_ERR_WORKSPACE_TOO_SMALL;
+    a.x = x, a.params = params, a.dout = dout, a.ws = (float*)workspace;
+    int grid = 0;
+    int rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
+    if (rc != IMPALA_OK) return rc;
+    const int64_t total = a.lay.total;
+    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        a.ws, grad, grid, total);
+    return impala_launch_status();
+}

@@ -1,0 +1,347 @@
+// V-trace targets, the three losses and their closed-form backward
+// (reference learner.py:116-162 + helpers :298-321 + the non-MLP part of :175).
+//
+// One warp per trajectory, lanes across time.  A CTA owns kTraj = 8 consecutive
+// trajectories (one per warp) and walks the unroll backwards in chunks of TC (<=128)
+// steps: all 256 threads stage the chunk's (TC, 8[, A]) slices of the time-major
+// tensors into shared memory with row-contiguous global loads (8 floats = one 32-byte
+// sector per row of the scalar tensors, 8*A floats per row of the logits), each warp
+// then reads its own column (row stride 9 / 8*AP+1 floats -> bank-conflict free), runs
+// the backward recurrence as an affine-map suffix scan over the 32 lanes of each
+// 32-step pass (carry between passes and chunks in a register), computes loss terms and
+// gradients in registers, and the results go back through shared memory so the global
+// stores are row-contiguous as well.
+//
+// Reference quirks reproduced in IMPALA_MODE_REFERENCE:
+//   delta_t = rho_t (r_t + gamma v_{t+1} - v_0)                  learner.py:126  (v[:1])
+//   acc_i   = delta_i + disc_i c_i (acc_{i+1} - v_{i+1})          learner.py:130
+//   vs = acc + v (:131);  pg_t = rho_t (r_t + disc_t vs_{t+1} - v_t)   (:135)
+// i.e. the affine map F_i(x) = (delta_i - g_i v_{i+1}) + g_i x with g_i = disc_i c_i.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTraj = 8;             // trajectories (= warps) per CTA
+constexpr int kThreads = kTraj * 32;
+constexpr int kColStride = kTraj + 1;  // padded row stride of the scalar tiles
+
+struct VtArgs {
+    const float* cur_logits;
+    const float* beh_logits;
+    const int32_t* actions;
+    const float* rewards;
+    const uint8_t* done;
+    const int32_t* lens;
+    const float* v;
+    float* vs;
+    float* pg_adv;
+    float* dlogits;
+    float* dv;
+    double* scalars;
+    int T, B, A, TC, mode;
+    float gamma, rho_bar, c_bar, v_loss_c, policy_loss_c, entropy_c, inv_batch;
+};
+
+template <int AP, bool WITH_LOSS>
+__global__ void __launch_bounds__(kThreads) vtrace_kernel(VtArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int T = a.T, B = a.B, A = a.A, TC = a.TC;
+    const int b0 = blockIdx.x * kTraj;
+    const int LS = kTraj * AP + 1;  // logits tile row stride (odd -> conflict free)
+
+    float* s_v = smem;                           // [TC+1][9]
+    float* s_vs = s_v + (TC + 1) * kColStride;   // [TC+1][9]
+    float* s_dv = s_vs + (TC + 1) * kColStride;  // [TC+1][9]
+    float* s_r = s_dv + (TC + 1) * kColStride;   // [TC][9]   rewards in, pg_adv out
+    int* s_act = reinterpret_cast<int*>(s_r + TC * kColStride);  // [TC][9] action | done<<30
+    float* s_cur = reinterpret_cast<float*>(s_act + TC * kColStride);  // [TC][LS] logits in, dlogits out
+    float* s_beh = s_cur + TC * LS;                                    // [TC][LS]
+    __shared__ double s_red[kTraj][4];
+
+    const int b = b0 + w;
+    const bool live = b < B;
+    int L = 0;
+    float v0 = 0.f;
+    if (live) {
+        L = min(max(__ldg(a.lens + b), 0), T);
+        v0 = __ldg(a.v + b);  // V(x_0): the reference's v[:1]
+    }
+    const int nb = min(kTraj, B - b0);  // live columns of this CTA
+
+    double sum_vl = 0.0, sum_pl = 0.0, sum_ent = 0.0, sum_rw = 0.0;
+    float carry = 0.f;  // acc at the first index after the current pass
+    const int nchunks = (T + TC - 1) / TC;
+
+    for (int c = nchunks - 1; c >= 0; --c) {
+        const int t0 = c * TC;
+        __syncthreads();  // previous chunk's stores have drained the tiles
+        // ---- stage: row-contiguous global reads ----
+        for (int idx = tid; idx < (TC + 1) * kTraj; idx += kThreads) {
+            const int tt = idx / kTraj, col = idx - tt * kTraj;
+            const int t = t0 + tt;
+            s_v[tt * kColStride + col] =
+                (t <= T && col < nb) ? __ldg(a.v + (size_t)t * B + b0 + col) : 0.f;
+        }
+        for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
+            const int tt = idx / kTraj, col = idx - tt * kTraj;
+            const int t = t0 + tt;
+            const bool ok = t < T && col < nb;
+            const size_t g = (size_t)t * B + b0 + col;
+            s_r[tt * kColStride + col] = ok ? __ldg(a.rewards + g) : 0.f;
+            int packed = 0;
+            if (ok) packed = (__ldg(a.actions + g) & 0x3fffffff) | (__ldg(a.done + g) ? (1 << 30) : 0);
+            s_act[tt * kColStride + col] = packed;
+        }
+        {
+            const int rowlen = nb * A;  // contiguous floats per time step for this CTA
+            for (int idx = tid; idx < TC * rowlen; idx += kThreads) {
+                const int tt = idx / rowlen, rem = idx - tt * rowlen;
+                const int t = t0 + tt;
+                const int col = rem / A, k = rem - col * A;
+                float zc = 0.f, zb = 0.f;
+                if (t < T) {
+                    const size_t g = ((size_t)t * B + b0) * A + rem;
+                    zc = __ldg(a.cur_logits + g);
+                    zb = __ldg(a.beh_logits + g);
+                }
+                s_cur[tt * LS + col * AP + k] = zc;
+                s_beh[tt * LS + col * AP + k] = zb;
+            }
+        }
+        __syncthreads();
+
+        // ---- compute: this warp's trajectory, 32 steps per pass, last pass first ----
+        if (live) {
+            for (int p = TC / 32 - 1; p >= 0; --p) {
+                const int tt = p * 32 + lane;
+                const int t = t0 + tt;
+                const bool valid = t < L;
+                const float r = s_r[tt * kColStride + w];
+                const int packed = s_act[tt * kColStride + w];
+                const int act = packed & 0x3fffffff;
+                const bool dn = (packed >> 30) & 1;
+                const float v_t = s_v[tt * kColStride + w];
+                const float v_n = s_v[(tt + 1) * kColStride + w];
+                float z[AP], zb[AP];
+#pragma unroll
+                for (int k = 0; k < AP; ++k) {
+                    z[k] = s_cur[tt * LS + w * AP + k];
+                    zb[k] = s_beh[tt * LS + w * AP + k];
+                }
+                // log-softmax of both logit vectors (learner.py:298-303)
+                float mx = z[0], mxb = zb[0];
+#pragma unroll
+                for (int k = 1; k < AP; ++k)
+                    if (k < A) mx = fmaxf(mx, z[k]), mxb = fmaxf(mxb, zb[k]);
+                float se = 0.f, seb = 0.f;
+#pragma unroll
+                for (int k = 0; k < AP; ++k)
+                    if (k < A) se += expf(z[k] - mx), seb += expf(zb[k] - mxb);
+                const float lse = mx + logf(se), lseb = mxb + logf(seb);
+                float z_a = z[0], zb_a = zb[0];
+#pragma unroll
+                for (int k = 1; k < AP; ++k)
+                    if (k == act) z_a = z[k], zb_a = zb[k];
+                const float lp_cur = z_a - lse, lp_beh = zb_a - lseb;
+                const float ratio = expf(lp_cur - lp_beh);                     // :121-123
+                const float rho = valid ? fminf(ratio, a.rho_bar) : 0.f;       // :124
+                const float cc = valid ? fminf(ratio, a.c_bar) : 0.f;          // :125
+                const float disc = (valid && !dn) ? a.gamma : 0.f;             // :109
+                const float g = disc * cc;
+                float fa;  // affine map F(x) = fa + g x
+                if (a.mode == IMPALA_MODE_REFERENCE) {
+                    const float delta = rho * (r + a.gamma * v_n - v0);        // :126
+                    fa = delta - g * v_n;                                      // :130
+                } else {
+                    fa = rho * (r + disc * v_n - v_t);
+                }
+                // inclusive suffix composition over the lanes: (A,G) <- F_lane o ... o F_31
+                float sa = fa, sg = g;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float a2 = __shfl_down_sync(IMPALA_FULL_MASK, sa, off);
+                    const float g2 = __shfl_down_sync(IMPALA_FULL_MASK, sg, off);
+                    if (lane + off < 32) {
+                        sa = fmaf(sg, a2, sa);
+                        sg = sg * g2;
+                    }
+                }
+                const float acc_t = fmaf(sg, carry, sa);
+                float acc_n = __shfl_down_sync(IMPALA_FULL_MASK, acc_t, 1);
+                if (lane == 31) acc_n = carry;
+                carry = __shfl_sync(IMPALA_FULL_MASK, acc_t, 0);
+                const float vs_n = acc_n + v_n;                                // :131
+                const float pg = rho * (r + disc * vs_n - v_t);                // :135
+                s_vs[tt * kColStride + w] = (t <= L) ? acc_t + v_t : 0.f;
+                s_r[tt * kColStride + w] = pg;  // rho == 0 on padding
+                if (WITH_LOSS) {
+                    // d total / d v = v_loss_c (v - vs) / B = -v_loss_c acc / B  (:149, :306-307)
+                    s_dv[tt * kColStride + w] = valid ? -a.v_loss_c * a.inv_batch * acc_t : 0.f;
+                    float ent = 0.f;
+                    float lz[AP], pk[AP];
+#pragma unroll
+                    for (int k = 0; k < AP; ++k) {
+                        lz[k] = z[k] - lse;
+                        pk[k] = (k < A) ? expf(lz[k]) : 0.f;
+                        if (k < A) ent -= pk[k] * lz[k];                       // :310-314, :153
+                    }
+#pragma unroll
+                    for (int k = 0; k < AP; ++k) {
+                        const float onehot = (k == act) ? 1.f : 0.f;
+                        const float dz = a.inv_batch * (a.policy_loss_c * pg * (pk[k] - onehot) +
+                                                        a.entropy_c * pk[k] * (lz[k] + ent));
+                        s_cur[tt * LS + w * AP + k] = (valid && k < A) ? dz : 0.f;
+                    }
+                    if (valid) {
+                        sum_vl += 0.5 * (double)acc_t * (double)acc_t;
+                        sum_pl += (double)(-lp_cur * pg);                      // :317-321
+                        sum_ent += (double)ent;
+                        sum_rw += (double)r;                                   // :108
+                    }
+                }
+            }
+            // the row one past this chunk (index t0+TC) belongs to the next chunk, except the
+            // bootstrap row T when it is exactly the last chunk's extra row
+            if (c == nchunks - 1 && t0 + TC == T && lane == 0) {
+                s_vs[TC * kColStride + w] = (L == T) ? s_v[TC * kColStride + w] : 0.f;
+                if (WITH_LOSS) s_dv[TC * kColStride + w] = 0.f;
+            }
+        }
+        __syncthreads();
+
+        // ---- store: row-contiguous global writes ----
+        const int rows_v = (c == nchunks - 1 && t0 + TC == T) ? TC + 1 : TC;
+        for (int idx = tid; idx < rows_v * kTraj; idx += kThreads) {
+            const int tt = idx / kTraj, col = idx - tt * kTraj;
+            const int t = t0 + tt;
+            if (t <= T && col < nb) {
+                const size_t g = (size_t)t * B + b0 + col;
+                if (a.vs) a.vs[g] = s_vs[tt * kColStride + col];
+                if (WITH_LOSS) a.dv[g] = s_dv[tt * kColStride + col];
+            }
+        }
+        if (a.pg_adv) {
+            for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
+                const int tt = idx / kTraj, col = idx - tt * kTraj;
+                const int t = t0 + tt;
+                if (t < T && col < nb) a.pg_adv[(size_t)t * B + b0 + col] = s_r[tt * kColStride + col];
+            }
+        }
+        if (WITH_LOSS) {
+            const int rowlen = nb * A;
+            for (int idx = tid; idx < TC * rowlen; idx += kThreads) {
+                const int tt = idx / rowlen, rem = idx - tt * rowlen;
+                const int t = t0 + tt;
+                const int col = rem / A, k = rem - col * A;
+                if (t < T) a.dlogits[((size_t)t * B + b0) * A + rem] = s_cur[tt * LS + col * AP + k];
+            }
+        }
+    }
+
+    if (WITH_LOSS) {
+        sum_vl = warp_sum_f64(sum_vl);
+        sum_pl = warp_sum_f64(sum_pl);
+        sum_ent = warp_sum_f64(sum_ent);
+        sum_rw = warp_sum_f64(sum_rw);
+        if (lane == 0) {
+            s_red[w][0] = sum_vl, s_red[w][1] = sum_pl, s_red[w][2] = sum_ent, s_red[w][3] = sum_rw;
+        }
+        __syncthreads();
+        if (tid < 4) {
+            double s = 0.0;
+            for (int i = 0; i < kTraj; ++i) s += s_red[i][tid];
+            atomicAdd(a.scalars + tid, s * (double)a.inv_batch);
+        }
+    }
+}
+
+int pick_ap(int A) {
+    if (A <= 2) return 2;
+    if (A <= 4) return 4;
+    if (A <= 8) return 8;
+    if (A <= 16) return 16;
+    return 0;
+}
+
+size_t smem_bytes(int TC, int AP) {
+    const size_t LS = kTraj * AP + 1;
+    return ((size_t)3 * (TC + 1) * kColStride + (size_t)2 * TC * kColStride + (size_t)2 * TC * LS) *
+           sizeof(float);
+}
+
+template <bool WITH_LOSS>
+int launch(VtArgs& a, cudaStream_t st) {
+    if (a.T < 1 || a.B < 1 || a.A < 1) return IMPALA_ERR_BAD_ARG;
+    const int AP = pick_ap(a.A);
+    if (!AP) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+    int tc_max = AP <= 4 ? 128 : (AP == 8 ? 64 : 32);
+    int tc = (int)impala_round_up(a.T, 32);
+    a.TC = tc < tc_max ? tc : tc_max;
+    const size_t smem = smem_bytes(a.TC, AP);
+    const unsigned grid = (unsigned)((a.B + kTraj - 1) / kTraj);
+#define VT_LAUNCH(APV)                                                                           \
+    {                                                                                            \
+        auto k = vtrace_kernel<APV, WITH_LOSS>;                                                  \
+        static size_t opted_in = 48 * 1024; /* per instantiation; avoids API calls in capture */ \
+        if (smem > opted_in) {                                                                   \
+            cudaError_t e =                                                                      \
+                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                 \
+            opted_in = smem;                                                                     \
+        }                                                                                        \
+        k<<<grid, kThreads, smem, st>>>(a);                                                      \
+    }
+    switch (AP) {
+        case 2: VT_LAUNCH(2) break;
+        case 4: VT_LAUNCH(4) break;
+        case 8: VT_LAUNCH(8) break;
+        default: VT_LAUNCH(16) break;
+    }
+#undef VT_LAUNCH
+    return impala_launch_status();
+}
+
+}  // namespace
+
+extern "C" int impala_vtrace(const float* cur_logits, const float* beh_logits,
+                             const int32_t* actions, const float* rewards, const uint8_t* done,
+                             const int32_t* lens, const float* v, float* vs, float* pg_adv, int T,
+                             int B, int A, float gamma, float rho_bar, float c_bar, int mode,
+                             void* stream) {
+    if (!cur_logits || !beh_logits || !actions || !rewards || !done || !lens || !v || !vs || !pg_adv)
+        return IMPALA_ERR_BAD_ARG;
+    if (mode != IMPALA_MODE_REFERENCE && mode != IMPALA_MODE_PAPER) return IMPALA_ERR_BAD_ARG;
+    VtArgs a{};
+    a.cur_logits = cur_logits, a.beh_logits = beh_logits, a.actions = actions, a.rewards = rewards;
+    a.done = done, a.lens = lens, a.v = v, a.vs = vs, a.pg_adv = pg_adv;
+    a.T = T, a.B = B, a.A = A, a.mode = mode;
+    a.gamma = gamma, a.rho_bar = rho_bar, a.c_bar = c_bar;
+    return launch<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int impala_vtrace_loss(const float* cur_logits, const float* beh_logits,
+                                  const int32_t* actions, const float* rewards,
+                                  const uint8_t* done, const int32_t* lens, const float* v,
+                                  float* vs, float* pg_adv, float* dlogits, float* dv,
+                                  double* scalars, int T, int B, int A, float gamma, float rho_bar,
+                                  float c_bar, float v_loss_c, float policy_loss_c,
+                                  float entropy_c, float inv_batch, int mode, void* stream) {
+    if (!cur_logits || !beh_logits || !actions || !rewards || !done || !lens || !v || !dlogits ||
+        !dv || !scalars)
+        return IMPALA_ERR_BAD_ARG;
+    if (mode != IMPALA_MODE_REFERENCE && mode != IMPALA_MODE_PAPER) return IMPALA_ERR_BAD_ARG;
+    cudaError_t e = cudaMemsetAsync(scalars, 0, 4 * sizeof(double), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    VtArgs a{};
+    a.cur_logits = cur_logits, a.beh_logits = beh_logits, a.actions = actions, a.rewards = rewards;
+    a.done = done, a.lens = lens, a.v = v, a.vs = vs, a.pg_adv = pg_adv, a.dlogits = dlogits;
+    a.dv = dv, a.scalars = scalars;
+    a.T = T, a.B = B, a.A = A, a.mode = mode;
+    a.gamma = gamma, a.rho_bar = rho_bar, a.c_bar = c_bar;
+    a.v_loss_c = v_loss_c, a.policy_loss_c = policy_loss_c, a.entropy_c = entropy_c;
+    a.inv_batch = inv_batch;
+    return launch<true>(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,276 @@
+"""Host-side step engine of the B200 learner: buffers, streams, CUDA graph, allreduce.
+
+One `LearnerEngine` lives in the learner process of one GPU.  It owns every device
+buffer of the update path and enqueues, per learner step, exactly the C-ABI calls of
+include/impala_b200.h (PyTorch only provides device memory, streams and
+`torch.distributed`):
+
+    impala_ingest          pinned host slab -> device slab (one DMA)      learner.py:104-109,117
+    impala_mlp_forward x2  policy logits (T*B rows), values ((T+1)*B)      learner.py:112-113
+    impala_vtrace_loss     V-trace, 3 losses, dL/dlogits, dL/dv, scalars   learner.py:116-162
+    impala_mlp_backward x2 parameter gradients (float64)                   learner.py:175
+    [all_reduce]           one NCCL sum over [grads | scalars], N > 1 only (new)
+    impala_clip_adam       per-net clip + Adam + step counter              learner.py:176-183
+
+With `use_graph=True` the launch sequence between ingest and the (optional)
+collective, and the optimizer launch after it, are captured once into CUDA graphs and
+replayed each step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+PKEYS = ("model.0.weight", "model.0.bias", "model.3.weight", "model.3.bias")
+SCALAR_NAMES = ("value_fn_loss", "policy_loss", "policy_entropy", "batch_mean_reward")
+_BATCH_FIELDS = (("obs", np.float32), ("beh_logits", np.float32), ("actions", np.int32),
+                 ("rewards", np.float32), ("done", np.uint8), ("lens", np.int32))
+_TORCH_DT = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8}
+
+
+def _ptr(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+class LearnerEngine:
+    def __init__(self, T: int, B_local: int, O: int, A: int, H_pi: int, H_v: int, hp,
+                 global_batch: int | None = None, device: str | torch.device = "cuda:0",
+                 mode: str = "reference", process_group=None, use_graph: bool = True,
+                 host_slabs: int = 2):
+        if not torch.cuda.is_available():
+            raise _cabi.ImpalaCudaError("LearnerEngine needs a CUDA device; there is no CPU path")
+        self.lib = _cabi.lib()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.T, self.B, self.O, self.A, self.H_pi, self.H_v = T, B_local, O, A, H_pi, H_v
+        self.hp = hp
+        self.mode = _cabi.MODES[mode]
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+
+            self.world = dist.get_world_size(process_group)
+        self.global_batch = int(global_batch if global_batch is not None else B_local * self.world)
+        self.inv_batch = 1.0 / self.global_batch
+        self.use_graph = use_graph
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.launches_per_step = 0
+
+        # ---- parameter blocks: [policy | value_fn], float32, 128-byte aligned tensors
+        self.pi_off, self.n_pi = _cabi.param_layout(O, H_pi, A)
+        self.vf_off, self.n_vf = _cabi.param_layout(O, H_v, 1)
+        self.n_total = self.n_pi + self.n_vf
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.params = torch.zeros(self.n_total, **f32)
+        self.adam_m = torch.zeros(self.n_total, **f32)
+        self.adam_v = torch.zeros(self.n_total, **f32)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        # float64 [gradient | 4 loss scalars | pad]: the all-reduce payload
+        self.comm = torch.zeros(self.n_total + 8, dtype=torch.float64, device=self.dev)
+        self.norms = torch.zeros(2, dtype=torch.float64, device=self.dev)
+
+        # ---- batch slab (device) and pinned staging slabs (host), identical layouts
+        self.slab_off, self.slab_bytes = _cabi.batch_layout(T, B_local, O, A)
+        self.d_slab = torch.zeros(self.slab_bytes, dtype=torch.uint8, device=self.dev)
+        self.h_slabs = [torch.zeros(self.slab_bytes, dtype=torch.uint8).pin_memory()
+                        for _ in range(host_slabs)]
+        shapes = {"obs": (T + 1, B_local, O), "beh_logits": (T, B_local, A),
+                  "actions": (T, B_local), "rewards": (T, B_local), "done": (T, B_local),
+                  "lens": (B_local,)}
+        self.shapes = shapes
+        self.d = {}
+        for (name, dt), off in zip(_BATCH_FIELDS, self.slab_off):
+            n = int(np.prod(shapes[name])) * np.dtype(dt).itemsize
+            self.d[name] = self.d_slab[off:off + n].view(_TORCH_DT[dt]).view(shapes[name])
+        self.h_views = []
+        for slab in self.h_slabs:
+            arr = slab.numpy()
+            views = {}
+            for (name, dt), off in zip(_BATCH_FIELDS, self.slab_off):
+                n = int(np.prod(shapes[name])) * np.dtype(dt).itemsize
+                views[name] = arr[off:off + n].view(dt).reshape(shapes[name])
+            self.h_views.append(views)
+
+        # ---- activations / gradients of the non-MLP part
+        self.logits = torch.zeros(T, B_local, A, **f32)
+        self.values = torch.zeros(T + 1, B_local, **f32)
+        self.vs = torch.zeros(T + 1, B_local, **f32)
+        self.pg_adv = torch.zeros(T, B_local, **f32)
+        self.dlogits = torch.zeros(T, B_local, A, **f32)
+        self.dv = torch.zeros(T + 1, B_local, **f32)
+        self.M_pi, self.M_vf = T * B_local, (T + 1) * B_local
+        self.ws_pi_bytes = self._ws_bytes(self.M_pi, O, H_pi, A)
+        self.ws_vf_bytes = self._ws_bytes(self.M_vf, O, H_v, 1)
+        self.ws_pi = torch.zeros(self.ws_pi_bytes, dtype=torch.uint8, device=self.dev)
+        self.ws_vf = torch.zeros(self.ws_vf_bytes, dtype=torch.uint8, device=self.dev)
+        self.h_scalars = torch.zeros(8, dtype=torch.float64).pin_memory()
+
+        self._graph_main = None
+        self._graph_opt = None
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _ws_bytes(self, M, O, H, N2):
+        n = self.lib.impala_mlp_backward_workspace(M, O, H, N2)
+        if n < 0:
+            _cabi.check(int(n), f"impala_mlp_backward_workspace(M={M},O={O},H={H},N2={N2})")
+        return int(n)
+
+    def _segments(self):
+        """(group, key, flat offset, shape) of every parameter tensor in `self.params`."""
+        O, A = self.O, self.A
+        shp_pi = ((self.H_pi, O), (self.H_pi,), (A, self.H_pi), (A,))
+        shp_vf = ((self.H_v, O), (self.H_v,), (1, self.H_v), (1,))
+        for key, off, shp in zip(PKEYS, self.pi_off, shp_pi):
+            yield "policy", key, off, shp
+        for key, off, shp in zip(PKEYS, self.vf_off, shp_vf):
+            yield "value_fn", key, self.n_pi + off, shp
+
+    def load_state(self, state: dict) -> None:
+        """state = {"policy": state_dict, "value_fn": state_dict} (any float dtype, CPU)."""
+        flat = torch.zeros(self.n_total, dtype=torch.float32)
+        for grp, key, off, shp in self._segments():
+            t = torch.as_tensor(np.asarray(state[grp][key]) if not torch.is_tensor(state[grp][key])
+                                else state[grp][key].detach().cpu())
+            if tuple(t.shape) != tuple(shp):
+                raise ValueError(f"{grp}.{key}: expected {shp}, got {tuple(t.shape)}")
+            flat[off:off + t.numel()] = t.reshape(-1).to(torch.float32)
+        self.params.copy_(flat)
+        torch.cuda.synchronize(self.dev)
+
+    def state(self, dtype=torch.float64) -> dict:
+        """Reference-format state_dicts (CPU, float64 like reference models.py:6)."""
+        self.stream.synchronize()
+        flat = self.params.detach().cpu()
+        out = {"policy": {}, "value_fn": {}}
+        for grp, key, off, shp in self._segments():
+            n = int(np.prod(shp))
+            out[grp][key] = flat[off:off + n].reshape(shp).to(dtype).clone()
+        return out
+
+    def grads(self) -> dict:
+        """Last step's pre-clip gradient (float64), reference state_dict layout."""
+        self.stream.synchronize()
+        flat = self.comm[: self.n_total].detach().cpu()
+        out = {"policy": {}, "value_fn": {}}
+        for grp, key, off, shp in self._segments():
+            n = int(np.prod(shp))
+            out[grp][key] = flat[off:off + n].reshape(shp).numpy().copy()
+        return out
+
+    # ---------------------------------------------------------------------- ingest
+    def host_batch(self, slot: int = 0) -> dict:
+        """Writable numpy views of pinned staging slab `slot` (fill these, then ingest)."""
+        return self.h_views[slot]
+
+    def fill_host(self, batch: dict, slot: int = 0) -> None:
+        for name, _ in _BATCH_FIELDS:
+            np.copyto(self.h_views[slot][name], batch[name])
+
+    def ingest(self, slot: int = 0) -> None:
+        _cabi.check(self.lib.impala_ingest(_ptr(self.d_slab), C.c_void_p(self.h_slabs[slot].data_ptr()),
+                                           self.slab_bytes, C.c_void_p(self.stream.cuda_stream)),
+                    "impala_ingest")
+
+    def load_device_batch(self, batch: dict) -> None:
+        """Convenience for kernel-only timing: put a batch in HBM without the staging slab."""
+        self.fill_host(batch, 0)
+        self.ingest(0)
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------------ step
+    def _enqueue_main(self) -> int:
+        lib, hp, st = self.lib, self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        T, B, O, A = self.T, self.B, self.O, self.A
+        p_pi = C.c_void_p(self.params.data_ptr())
+        p_vf = C.c_void_p(self.params.data_ptr() + 4 * self.n_pi)
+        g_pi = C.c_void_p(self.comm.data_ptr())
+        g_vf = C.c_void_p(self.comm.data_ptr() + 8 * self.n_pi)
+        scal = C.c_void_p(self.comm.data_ptr() + 8 * self.n_total)
+        obs = _ptr(self.d["obs"])
+        _cabi.check(lib.impala_mlp_forward(obs, p_pi, _ptr(self.logits), self.M_pi, O, self.H_pi, A, st),
+                    "impala_mlp_forward(policy)")
+        _cabi.check(lib.impala_mlp_forward(obs, p_vf, _ptr(self.values), self.M_vf, O, self.H_v, 1, st),
+                    "impala_mlp_forward(value_fn)")
+        _cabi.check(lib.impala_vtrace_loss(
+            _ptr(self.logits), _ptr(self.d["beh_logits"]), _ptr(self.d["actions"]),
+            _ptr(self.d["rewards"]), _ptr(self.d["done"]), _ptr(self.d["lens"]), _ptr(self.values),
+            _ptr(self.vs), _ptr(self.pg_adv), _ptr(self.dlogits), _ptr(self.dv), scal, T, B, A,
+            float(hp.gamma), float(hp.rho_bar), float(hp.c_bar), float(hp.v_loss_c),
+            float(hp.policy_loss_c), float(hp.entropy_c), float(self.inv_batch), self.mode, st),
+            "impala_vtrace_loss")
+        _cabi.check(lib.impala_mlp_backward(obs, p_pi, _ptr(self.dlogits), g_pi, _ptr(self.ws_pi),
+                                            self.ws_pi_bytes, self.M_pi, O, self.H_pi, A, st),
+                    "impala_mlp_backward(policy)")
+        _cabi.check(lib.impala_mlp_backward(obs, p_vf, _ptr(self.dv), g_vf, _ptr(self.ws_vf),
+                                            self.ws_vf_bytes, self.M_vf, O, self.H_v, 1, st),
+                    "impala_mlp_backward(value_fn)")
+        return 7  # 2 fwd + 1 vtrace_loss + 2 x (bwd + partial reduce)
+
+    def _enqueue_opt(self) -> int:
+        hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _cabi.check(self.lib.impala_clip_adam(
+            _ptr(self.params), _ptr(self.comm), _ptr(self.adam_m), _ptr(self.adam_v),
+            _ptr(self.adam_step), self.n_pi, self.n_total, float(hp.max_norm),
+            float(0.95 * hp.lr),  # LambdaLR(lambda e: 0.95): constant factor, learner.py:42
+            0.9, 0.999, 1e-8, _ptr(self.norms), st), "impala_clip_adam")
+        return 1
+
+    def _capture(self):
+        with torch.cuda.stream(self.stream):
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, stream=self.stream):
+                self._enqueue_main()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=self.stream):
+                self._enqueue_opt()
+        self._graph_main, self._graph_opt = g1, g2
+
+    def step(self) -> None:
+        """One learner update on the batch currently in the device slab (async)."""
+        with torch.cuda.stream(self.stream):
+            if self.use_graph and self.steps_done >= 1:
+                if self._graph_main is None:
+                    self._capture()
+                self._graph_main.replay()
+                n = 7
+            else:
+                n = self._enqueue_main()  # first step eager: fills the launch-config caches
+            if self.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.use_graph and self._graph_opt is not None:
+                self._graph_opt.replay()
+                n += 1
+            else:
+                n += self._enqueue_opt()
+        self.launches_per_step = n
+        self.steps_done += 1
+
+    def forward_backward_only(self) -> None:
+        """Everything up to (not including) the collective and the optimizer - for tests."""
+        with torch.cuda.stream(self.stream):
+            self._enqueue_main()
+
+    def read_scalars(self) -> dict:
+        """D2H of the step's logged numbers (learner.py:217-240); synchronises the stream."""
+        with torch.cuda.stream(self.stream):
+            self.h_scalars[:4].copy_(self.comm[self.n_total:self.n_total + 4], non_blocking=True)
+            self.h_scalars[4:6].copy_(self.norms, non_blocking=True)
+        self.stream.synchronize()
+        s = self.h_scalars.tolist()
+        hp = self.hp
+        out = dict(zip(SCALAR_NAMES, s[:4]))
+        out["total_loss"] = (hp.v_loss_c * out["value_fn_loss"] + hp.policy_loss_c * out["policy_loss"]
+                             - hp.entropy_c * out["policy_entropy"])  # learner.py:154-159
+        out["norm_policy"], out["norm_value"] = s[4], s[5]
+        return out
+
+    def synchronize(self) -> None:
+        self.stream.synchronize()
