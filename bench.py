@@ -76,15 +76,21 @@ def time_cpu_port(sample_B: int, warm: int, timed: int, threads: int):
 
 
 def cpu_baseline(sample_B=512, warm=1, timed=3):
+    """1 torch thread on the full sample; all host threads probed on a small sample first -
+    the per-trajectory python loop gets slower with more threads (tiny ops, thread thrash), so the
+    many-thread run is only repeated at full sample size if the probe says it could win."""
     cores = os.cpu_count() or 1
     t1 = time_cpu_port(sample_B, warm, timed, 1)
-    tn = time_cpu_port(sample_B, warm, timed, cores) if cores > 1 else t1
+    probe_B = 32
+    tn_probe = time_cpu_port(probe_B, 1, 1, cores) * (sample_B / probe_B) if cores > 1 else t1
+    tn = time_cpu_port(sample_B, warm, timed, cores) if tn_probe < t1 else tn_probe
     best_t, best_c = (t1, 1) if t1 <= tn else (tn, cores)
     scale = WORKLOAD["B"] / sample_B  # cost is linear in B (python loop over trajectories)
     return dict(value=1.0 / (best_t * scale), unit="steps/s", cores=best_c, kind="port",
                 sample=(f"oracle/cpu_learner_port.py, {warm}+{timed} updates of B={sample_B} "
                         f"(T=20,O=24,H=256), median, scaled x{scale:g} to B=4096 (cost linear in B); "
-                        f"1 thread {t1 * 1e3:.0f} ms, {cores} threads {tn * 1e3:.0f} ms per B={sample_B} update"),
+                        f"1 thread {t1 * 1e3:.0f} ms per B={sample_B} update; {cores} threads "
+                        f"{tn * 1e3:.0f} ms ({'measured' if tn_probe < t1 else f'extrapolated from a B={probe_B} probe'})"),
                 host_cores=cores)
 
 
@@ -114,10 +120,20 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        # nvidia-smi needs a few hundred ms before its first line; wait so short runs get samples
+        t_end = time.time() + 5.0
+        while self.p is not None and time.time() < t_end and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.05)
+        self.skip = 0
+
+    def mark(self):
+        """Discard everything sampled so far (idle clocks before the GPU is under load)."""
+        self.f.flush()
+        self.skip = os.path.getsize(self.f.name)
 
     def stop(self):
         if self.p is None:
@@ -128,7 +144,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(self.skip)
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ln in self.f.read().splitlines():
@@ -176,7 +192,8 @@ def kernel_breakdown(eng, flush, iters=20):
         "vtrace_loss": lambda: lib.impala_vtrace_loss(
             _ptr(eng.logits), _ptr(eng.d["beh_logits"]), _ptr(eng.d["actions"]), _ptr(eng.d["rewards"]),
             _ptr(eng.d["done"]), _ptr(eng.d["lens"]), _ptr(eng.values), _ptr(eng.vs), _ptr(eng.pg_adv),
-            _ptr(eng.dlogits), _ptr(eng.dv), scal, T, B, A, float(hp.gamma), float(hp.rho_bar),
+            _ptr(eng.dlogits), _ptr(eng.dv), scal, _ptr(eng.ws_vt), eng.ws_vt_bytes, T, B, A,
+            float(hp.gamma), float(hp.rho_bar),
             float(hp.c_bar), float(hp.v_loss_c), float(hp.policy_loss_c), float(hp.entropy_c),
             float(eng.inv_batch), eng.mode, st),
         "mlp_backward(policy)": lambda: lib.impala_mlp_backward(obs, p_pi, _ptr(eng.dlogits), g_pi, _ptr(eng.ws_pi), eng.ws_pi_bytes, eng.M_pi, O, eng.H_pi, A, st),
@@ -281,12 +298,15 @@ def run_own_arm(args):
     # ---------------- device-resident ("value") ----------------
     eng.ingest(0)
     eng.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
     with torch.cuda.stream(eng.stream):
-        for _ in range(max(3, args.warmup)):
+        for i in range(max(3, args.warmup)):
             flush()
             eng.step()
+            if i == 0 and sampler:
+                torch.cuda.synchronize()
+                sampler.mark()  # clocks are sampled from here to the end of the e2e loop
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     evs = []
     with torch.cuda.stream(eng.stream):
         for _ in range(args.steps):
@@ -302,18 +322,31 @@ def run_own_arm(args):
     scal_dev = eng.read_scalars()
 
     # ---------------- end to end through host buffers ----------------
-    for i in range(max(3, args.warmup)):
-        eng.ingest(i % 2)
-        eng.step()
-        eng.read_scalars()
+    # software pipeline: the DMA of batch i+1 (copy stream) runs under the kernels of batch i;
+    # the host reads step i-1's scalars while step i runs.  Every step's H2D and D2H happen
+    # inside the timed region.
+    def e2e_loop(n):
+        last = None
+        eng.ingest(0)
+        prev = None
+        for i in range(n):
+            if i + 1 < n:
+                eng.ingest((i + 1) % 2)   # H2D of the next step's inputs from pinned memory
+            eng.step(i % 2)
+            tk = eng.post_scalars()       # D2H of this step's loss scalars
+            if prev is not None:
+                last = eng.fetch_scalars(prev)
+            prev = tk
+        last = eng.fetch_scalars(prev)
+        eng.synchronize()
+        return last
+
+    e2e_loop(max(3, args.warmup))
     barrier()
     t0 = time.perf_counter()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(eng.stream)
-    for i in range(args.steps):
-        eng.ingest(i % 2)        # H2D of this step's inputs from pinned memory
-        eng.step()
-        last = eng.read_scalars()  # D2H of the step's loss scalars (synchronises)
+    last = e2e_loop(args.steps)
     e_stop.record(eng.stream)
     barrier()
     e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -374,7 +407,8 @@ def run_own_arm(args):
         e2e=dict(value=args.steps / (e2e_wall_ms * 1e-3), unit="steps/s",
                  h2d_bytes_per_step=int(eng.slab_bytes) * world, d2h_bytes_per_step=48 * world,
                  ms_per_step_wall=e2e_wall_ms / args.steps, ms_per_step_device=e2e_dev_ms / args.steps,
-                 note="wall clock around K x (H2D from pinned slab, step, D2H of scalars), max over ranks"),
+                 note=("wall clock around K x (H2D from pinned slab, step, D2H of scalars), max over ranks; "
+                       "copy of batch i+1 overlaps compute of batch i (double-buffered slabs)")),
         roofline=roofline, kernels=kernels,
         loss=dict(device_resident=scal_dev["total_loss"], e2e_last=last["total_loss"]),
     )

@@ -87,20 +87,26 @@ int impala_vtrace(const float* cur_logits, const float* beh_logits, const int32_
                   float* vs, float* pg_adv, int T, int B, int A, float gamma, float rho_bar,
                   float c_bar, int mode, void* stream);
 
+/* Bytes of scratch impala_vtrace_loss needs.  The caller zero-fills it ONCE after
+ * allocation; every call leaves it zeroed where it must be (self-re-arming counter). */
+int64_t impala_vtrace_loss_workspace(int T, int B, int A);
+
 /* V-trace + the three losses + their closed-form backward in one kernel
  * (learner.py:116-162 and the non-MLP part of :175; helper functions :298-321).
  *   dlogits (T,B,A), dv (T+1,B): d total_loss / d logits, d total_loss / d v
- *   scalars[0..4) (float64, zeroed by this call, then atomically accumulated):
- *     value_fn_loss, policy_loss, policy_entropy (each sum_b(..)*inv_batch as logged at
- *     learner.py:160-162) and batch_mean_reward (:108).
+ *   scalars[0..4) (float64, overwritten): value_fn_loss, policy_loss, policy_entropy (each
+ *     sum_b(..)*inv_batch as logged at learner.py:160-162) and batch_mean_reward (:108);
+ *     per-CTA sums are combined in a fixed order by the last CTA to finish, so the four
+ *     numbers are bitwise reproducible.
  *   vs / pg_adv may be NULL when the caller does not need them.
  *   inv_batch = 1 / GLOBAL batch size (all ranks), so shard results add up. */
 int impala_vtrace_loss(const float* cur_logits, const float* beh_logits, const int32_t* actions,
                        const float* rewards, const uint8_t* done, const int32_t* lens,
                        const float* v, float* vs, float* pg_adv, float* dlogits, float* dv,
-                       double* scalars, int T, int B, int A, float gamma, float rho_bar,
-                       float c_bar, float v_loss_c, float policy_loss_c, float entropy_c,
-                       float inv_batch, int mode, void* stream);
+                       double* scalars, void* workspace, int64_t workspace_bytes, int T, int B,
+                       int A, float gamma, float rho_bar, float c_bar, float v_loss_c,
+                       float policy_loss_c, float entropy_c, float inv_batch, int mode,
+                       void* stream);
 
 /* Per-group gradient clipping + Adam in one launch (learner.py:176-183).
  *   params/m/v: f32 [n_total]; grad: f64 [n_total] (the possibly all-reduced sum);

@@ -1,0 +1,16 @@
+"""GPU: the drop-in Learner as a forked process behind a real mp.Queue (boundary)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_learner_process_end_to_end(tmp_path):
+    script = os.path.join(os.path.dirname(__file__), "learner_process_check.py")
+    res = subprocess.run([sys.executable, script, str(tmp_path / "logs")], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "LEARNER_PROCESS_OK" in res.stdout

@@ -205,7 +205,7 @@ def test_engine_updates_match_reference(golden, use_graph):
     for u in range(golden.updates):
         eng.fill_host(golden.batch(u), u % 2)
         eng.ingest(u % 2)
-        eng.step()
+        eng.step(u % 2)
         sc = eng.read_scalars()
         ref = golden.scalars(u)
         for k in ("value_fn_loss", "policy_loss", "policy_entropy", "total_loss", "batch_mean_reward"):

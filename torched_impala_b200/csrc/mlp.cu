@@ -29,13 +29,37 @@ struct GridInfo {
 std::mutex g_cfg_mutex;
 std::map<std::tuple<const void*, int, int, size_t>, GridInfo> g_cfg_cache;
 
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, double* __restrict__ grad,
-                                       int nparts, int64_t total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += (double)ws[(size_t)c * total + i];
-    grad[i] = s;
+// grad[i] = sum_c ws[c][i] in float64.  A CTA covers 32 consecutive entries (one 128-byte
+// line per partial row); its 8 warps split the partial rows, so every load instruction is
+// one fully coalesced line and 8 x 4 loads are in flight per entry.  Fixed summation
+// order -> bitwise reproducible gradients.
+constexpr int kRedWarps = 8;
+__global__ void __launch_bounds__(kRedWarps * 32)
+reduce_partials_kernel(const float* __restrict__ ws, double* __restrict__ grad, int nparts,
+                       int64_t total) {
+    __shared__ double s_sum[kRedWarps][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (i < total) {
+        int c = g;
+        for (; c + 3 * kRedWarps < nparts; c += 4 * kRedWarps) {
+            const float a0 = __ldg(ws + (size_t)c * total + i);
+            const float a1 = __ldg(ws + (size_t)(c + kRedWarps) * total + i);
+            const float a2 = __ldg(ws + (size_t)(c + 2 * kRedWarps) * total + i);
+            const float a3 = __ldg(ws + (size_t)(c + 3 * kRedWarps) * total + i);
+            s0 += a0, s1 += a1, s2 += a2, s3 += a3;
+        }
+        for (; c < nparts; c += kRedWarps) s0 += __ldg(ws + (size_t)c * total + i);
+    }
+    s_sum[g][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (g == 0 && i < total) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kRedWarps; ++w) s += s_sum[w][lane];
+        grad[i] = s;
+    }
 }
 
 bool pick_config(int O, int H, int N2, bool bwd, MlpConfig* c) {
@@ -155,7 +179,7 @@ extern "C" int impala_mlp_backward(const float* x, const float* params, const fl
     int rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
     if (rc != IMPALA_OK) return rc;
     const int64_t total = a.lay.total;
-    reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        a.ws, grad, grid, total);
+    reduce_partials_kernel<<<(unsigned)((total + 31) / 32), kRedWarps * 32, 0,
+                             (cudaStream_t)stream>>>(a.ws, grad, grid, total);
     return impala_launch_status();
 }

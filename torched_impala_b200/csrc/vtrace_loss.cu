@@ -40,11 +40,13 @@ struct VtArgs {
     float* dlogits;
     float* dv;
     double* scalars;
+    double* partials;        // [gridDim.x][4] per-CTA loss sums (workspace)
+    unsigned int* counter;   // CTA arrival counter (workspace; zero on entry, zero on exit)
     int T, B, A, TC, mode;
     float gamma, rho_bar, c_bar, v_loss_c, policy_loss_c, entropy_c, inv_batch;
 };
 
-template <int AP, bool WITH_LOSS>
+template <int AP, bool WITH_LOSS, bool VEC>
 __global__ void __launch_bounds__(kThreads) vtrace_kernel(VtArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -78,24 +80,68 @@ __global__ void __launch_bounds__(kThreads) vtrace_kernel(VtArgs a) {
     for (int c = nchunks - 1; c >= 0; --c) {
         const int t0 = c * TC;
         __syncthreads();  // previous chunk's stores have drained the tiles
-        // ---- stage: row-contiguous global reads ----
-        for (int idx = tid; idx < (TC + 1) * kTraj; idx += kThreads) {
-            const int tt = idx / kTraj, col = idx - tt * kTraj;
-            const int t = t0 + tt;
-            s_v[tt * kColStride + col] =
-                (t <= T && col < nb) ? __ldg(a.v + (size_t)t * B + b0 + col) : 0.f;
-        }
-        for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
-            const int tt = idx / kTraj, col = idx - tt * kTraj;
-            const int t = t0 + tt;
-            const bool ok = t < T && col < nb;
-            const size_t g = (size_t)t * B + b0 + col;
-            s_r[tt * kColStride + col] = ok ? __ldg(a.rewards + g) : 0.f;
-            int packed = 0;
-            if (ok) packed = (__ldg(a.actions + g) & 0x3fffffff) | (__ldg(a.done + g) ? (1 << 30) : 0);
-            s_act[tt * kColStride + col] = packed;
-        }
-        {
+        // ---- stage: row-contiguous global reads (128-bit when B % 8 == 0) ----
+        if constexpr (VEC) {
+            for (int idx = tid; idx < (TC + 1) * 2; idx += kThreads) {
+                const int tt = idx >> 1, h = idx & 1, t = t0 + tt;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t <= T) x = __ldg(reinterpret_cast<const float4*>(a.v + (size_t)t * B + b0) + h);
+                float* d = s_v + tt * kColStride + 4 * h;
+                d[0] = x.x, d[1] = x.y, d[2] = x.z, d[3] = x.w;
+            }
+            for (int idx = tid; idx < TC * 2; idx += kThreads) {
+                const int tt = idx >> 1, h = idx & 1, t = t0 + tt;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                int4 ac = make_int4(0, 0, 0, 0);
+                uchar4 dn = make_uchar4(0, 0, 0, 0);
+                if (t < T) {
+                    const size_t g = (size_t)t * B + b0;
+                    r = __ldg(reinterpret_cast<const float4*>(a.rewards + g) + h);
+                    ac = __ldg(reinterpret_cast<const int4*>(a.actions + g) + h);
+                    dn = __ldg(reinterpret_cast<const uchar4*>(a.done + g) + h);
+                }
+                float* dr = s_r + tt * kColStride + 4 * h;
+                int* da = s_act + tt * kColStride + 4 * h;
+                dr[0] = r.x, dr[1] = r.y, dr[2] = r.z, dr[3] = r.w;
+                da[0] = (ac.x & 0x3fffffff) | (dn.x ? (1 << 30) : 0);
+                da[1] = (ac.y & 0x3fffffff) | (dn.y ? (1 << 30) : 0);
+                da[2] = (ac.z & 0x3fffffff) | (dn.z ? (1 << 30) : 0);
+                da[3] = (ac.w & 0x3fffffff) | (dn.w ? (1 << 30) : 0);
+            }
+            const int q4 = 2 * A;  // float4 per time step: 8 trajectories x A logits
+            for (int idx = tid; idx < TC * q4; idx += kThreads) {
+                const int tt = idx / q4, q = idx - tt * q4, t = t0 + tt;
+                float4 zc = make_float4(0.f, 0.f, 0.f, 0.f), zb = zc;
+                if (t < T) {
+                    const size_t g = ((size_t)t * B + b0) * A;
+                    zc = __ldg(reinterpret_cast<const float4*>(a.cur_logits + g) + q);
+                    zb = __ldg(reinterpret_cast<const float4*>(a.beh_logits + g) + q);
+                }
+                const float c4[4] = {zc.x, zc.y, zc.z, zc.w}, b4[4] = {zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int rem = 4 * q + e, col = rem / A, k = rem - col * A;
+                    s_cur[tt * LS + col * AP + k] = c4[e];
+                    s_beh[tt * LS + col * AP + k] = b4[e];
+                }
+            }
+        } else {
+            for (int idx = tid; idx < (TC + 1) * kTraj; idx += kThreads) {
+                const int tt = idx / kTraj, col = idx - tt * kTraj;
+                const int t = t0 + tt;
+                s_v[tt * kColStride + col] =
+                    (t <= T && col < nb) ? __ldg(a.v + (size_t)t * B + b0 + col) : 0.f;
+            }
+            for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
+                const int tt = idx / kTraj, col = idx - tt * kTraj;
+                const int t = t0 + tt;
+                const bool ok = t < T && col < nb;
+                const size_t g = (size_t)t * B + b0 + col;
+                s_r[tt * kColStride + col] = ok ? __ldg(a.rewards + g) : 0.f;
+                int packed = 0;
+                if (ok) packed = (__ldg(a.actions + g) & 0x3fffffff) | (__ldg(a.done + g) ? (1 << 30) : 0);
+                s_act[tt * kColStride + col] = packed;
+            }
             const int rowlen = nb * A;  // contiguous floats per time step for this CTA
             for (int idx = tid; idx < TC * rowlen; idx += kThreads) {
                 const int tt = idx / rowlen, rem = idx - tt * rowlen;
@@ -214,34 +260,79 @@ __global__ void __launch_bounds__(kThreads) vtrace_kernel(VtArgs a) {
 
         // ---- store: row-contiguous global writes ----
         const int rows_v = (c == nchunks - 1 && t0 + TC == T) ? TC + 1 : TC;
-        for (int idx = tid; idx < rows_v * kTraj; idx += kThreads) {
-            const int tt = idx / kTraj, col = idx - tt * kTraj;
-            const int t = t0 + tt;
-            if (t <= T && col < nb) {
-                const size_t g = (size_t)t * B + b0 + col;
-                if (a.vs) a.vs[g] = s_vs[tt * kColStride + col];
-                if (WITH_LOSS) a.dv[g] = s_dv[tt * kColStride + col];
+        if constexpr (VEC) {
+            for (int idx = tid; idx < rows_v * 2; idx += kThreads) {
+                const int tt = idx >> 1, h = idx & 1, t = t0 + tt;
+                if (t <= T) {
+                    const size_t g = (size_t)t * B + b0;
+                    const float* sv = s_vs + tt * kColStride + 4 * h;
+                    if (a.vs) reinterpret_cast<float4*>(a.vs + g)[h] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                    if (WITH_LOSS) {
+                        const float* sd = s_dv + tt * kColStride + 4 * h;
+                        reinterpret_cast<float4*>(a.dv + g)[h] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+                    }
+                }
             }
-        }
-        if (a.pg_adv) {
-            for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
+            if (a.pg_adv) {
+                for (int idx = tid; idx < TC * 2; idx += kThreads) {
+                    const int tt = idx >> 1, h = idx & 1, t = t0 + tt;
+                    if (t < T) {
+                        const float* sp = s_r + tt * kColStride + 4 * h;
+                        reinterpret_cast<float4*>(a.pg_adv + (size_t)t * B + b0)[h] =
+                            make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    }
+                }
+            }
+            if (WITH_LOSS) {
+                const int q4 = 2 * A;
+                for (int idx = tid; idx < TC * q4; idx += kThreads) {
+                    const int tt = idx / q4, q = idx - tt * q4, t = t0 + tt;
+                    if (t < T) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int rem = 4 * q + e, col = rem / A, k = rem - col * A;
+                            o[e] = s_cur[tt * LS + col * AP + k];
+                        }
+                        reinterpret_cast<float4*>(a.dlogits + ((size_t)t * B + b0) * A)[q] =
+                            make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+        } else {
+            for (int idx = tid; idx < rows_v * kTraj; idx += kThreads) {
                 const int tt = idx / kTraj, col = idx - tt * kTraj;
                 const int t = t0 + tt;
-                if (t < T && col < nb) a.pg_adv[(size_t)t * B + b0 + col] = s_r[tt * kColStride + col];
+                if (t <= T && col < nb) {
+                    const size_t g = (size_t)t * B + b0 + col;
+                    if (a.vs) a.vs[g] = s_vs[tt * kColStride + col];
+                    if (WITH_LOSS) a.dv[g] = s_dv[tt * kColStride + col];
+                }
             }
-        }
-        if (WITH_LOSS) {
-            const int rowlen = nb * A;
-            for (int idx = tid; idx < TC * rowlen; idx += kThreads) {
-                const int tt = idx / rowlen, rem = idx - tt * rowlen;
-                const int t = t0 + tt;
-                const int col = rem / A, k = rem - col * A;
-                if (t < T) a.dlogits[((size_t)t * B + b0) * A + rem] = s_cur[tt * LS + col * AP + k];
+            if (a.pg_adv) {
+                for (int idx = tid; idx < TC * kTraj; idx += kThreads) {
+                    const int tt = idx / kTraj, col = idx - tt * kTraj;
+                    const int t = t0 + tt;
+                    if (t < T && col < nb) a.pg_adv[(size_t)t * B + b0 + col] = s_r[tt * kColStride + col];
+                }
+            }
+            if (WITH_LOSS) {
+                const int rowlen = nb * A;
+                for (int idx = tid; idx < TC * rowlen; idx += kThreads) {
+                    const int tt = idx / rowlen, rem = idx - tt * rowlen;
+                    const int t = t0 + tt;
+                    const int col = rem / A, k = rem - col * A;
+                    if (t < T) a.dlogits[((size_t)t * B + b0) * A + rem] = s_cur[tt * LS + col * AP + k];
+                }
             }
         }
     }
 
     if (WITH_LOSS) {
+        // per-CTA sums -> workspace; the last CTA to arrive adds them up in a fixed order
+        // (bitwise reproducible, no float64 atomics, no memset node) and re-arms the counter.
+        __shared__ bool s_last;
+        __shared__ double s_fin[64][4];
         sum_vl = warp_sum_f64(sum_vl);
         sum_pl = warp_sum_f64(sum_pl);
         sum_ent = warp_sum_f64(sum_ent);
@@ -253,7 +344,26 @@ __global__ void __launch_bounds__(kThreads) vtrace_kernel(VtArgs a) {
         if (tid < 4) {
             double s = 0.0;
             for (int i = 0; i < kTraj; ++i) s += s_red[i][tid];
-            atomicAdd(a.scalars + tid, s * (double)a.inv_batch);
+            a.partials[(size_t)blockIdx.x * 4 + tid] = s;
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int which = tid & 3, stripe = tid >> 2;  // 64 stripes x 4 scalars
+            double s = 0.0;
+            for (unsigned cta = stripe; cta < gridDim.x; cta += 64)
+                s += __ldcg(a.partials + (size_t)cta * 4 + which);
+            s_fin[stripe][which] = s;
+            __syncthreads();
+            if (tid < 4) {
+                double tot = 0.0;
+                for (int i = 0; i < 64; ++i) tot += s_fin[i][tid];
+                a.scalars[tid] = tot * (double)a.inv_batch;
+            }
+            if (tid == 0) *a.counter = 0u;
         }
     }
 }
@@ -272,6 +382,8 @@ size_t smem_bytes(int TC, int AP) {
            sizeof(float);
 }
 
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <bool WITH_LOSS>
 int launch(VtArgs& a, cudaStream_t st) {
     if (a.T < 1 || a.B < 1 || a.A < 1) return IMPALA_ERR_BAD_ARG;
@@ -282,9 +394,16 @@ int launch(VtArgs& a, cudaStream_t st) {
     a.TC = tc < tc_max ? tc : tc_max;
     const size_t smem = smem_bytes(a.TC, AP);
     const unsigned grid = (unsigned)((a.B + kTraj - 1) / kTraj);
-#define VT_LAUNCH(APV)                                                                           \
+    const bool vec = a.B % kTraj == 0 && aligned16(a.cur_logits) && aligned16(a.beh_logits) &&
+                     aligned16(a.actions) && aligned16(a.rewards) && aligned16(a.v) &&
+                     aligned16(a.vs) && aligned16(a.pg_adv) && aligned16(a.dlogits) &&
+                     aligned16(a.dv) && (reinterpret_cast<uintptr_t>(a.done) & 3) == 0;
+#define VT_LAUNCH(APV)                 \
+    if (vec) VT_LAUNCH_V(APV, true)    \
+    else VT_LAUNCH_V(APV, false)
+#define VT_LAUNCH_V(APV, VECV)                                                                   \
     {                                                                                            \
-        auto k = vtrace_kernel<APV, WITH_LOSS>;                                                  \
+        auto k = vtrace_kernel<APV, WITH_LOSS, VECV>;                                            \
         static size_t opted_in = 48 * 1024; /* per instantiation; avoids API calls in capture */ \
         if (smem > opted_in) {                                                                   \
             cudaError_t e =                                                                      \
@@ -301,6 +420,7 @@ int launch(VtArgs& a, cudaStream_t st) {
         default: VT_LAUNCH(16) break;
     }
 #undef VT_LAUNCH
+#undef VT_LAUNCH_V
     return impala_launch_status();
 }
 
@@ -322,23 +442,35 @@ extern "C" int impala_vtrace(const float* cur_logits, const float* beh_logits,
     return launch<false>(a, (cudaStream_t)stream);
 }
 
+extern "C" int64_t impala_vtrace_loss_workspace(int T, int B, int A) {
+    if (T < 1 || B < 1 || A < 1) return IMPALA_ERR_BAD_ARG;
+    const int64_t grid = (B + kTraj - 1) / kTraj;
+    return grid * 4 * (int64_t)sizeof(double) + 16;  // per-CTA sums + arrival counter
+}
+
 extern "C" int impala_vtrace_loss(const float* cur_logits, const float* beh_logits,
                                   const int32_t* actions, const float* rewards,
                                   const uint8_t* done, const int32_t* lens, const float* v,
                                   float* vs, float* pg_adv, float* dlogits, float* dv,
-                                  double* scalars, int T, int B, int A, float gamma, float rho_bar,
-                                  float c_bar, float v_loss_c, float policy_loss_c,
-                                  float entropy_c, float inv_batch, int mode, void* stream) {
+                                  double* scalars, void* workspace, int64_t workspace_bytes, int T,
+                                  int B, int A, float gamma, float rho_bar, float c_bar,
+                                  float v_loss_c, float policy_loss_c, float entropy_c,
+                                  float inv_batch, int mode, void* stream) {
     if (!cur_logits || !beh_logits || !actions || !rewards || !done || !lens || !v || !dlogits ||
-        !dv || !scalars)
+        !dv || !scalars || !workspace)
         return IMPALA_ERR_BAD_ARG;
     if (mode != IMPALA_MODE_REFERENCE && mode != IMPALA_MODE_PAPER) return IMPALA_ERR_BAD_ARG;
-    cudaError_t e = cudaMemsetAsync(scalars, 0, 4 * sizeof(double), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
+    const int64_t need = impala_vtrace_loss_workspace(T, B, A);
+    if (need < 0) return (int)need;
+    if (workspace_bytes < need) return IMPALA_ERR_WORKSPACE_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) return IMPALA_ERR_BAD_ARG;
     VtArgs a{};
     a.cur_logits = cur_logits, a.beh_logits = beh_logits, a.actions = actions, a.rewards = rewards;
     a.done = done, a.lens = lens, a.v = v, a.vs = vs, a.pg_adv = pg_adv, a.dlogits = dlogits;
     a.dv = dv, a.scalars = scalars;
+    // workspace = [counter (16 bytes) | per-CTA sums]
+    a.counter = reinterpret_cast<unsigned int*>(workspace);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
     a.T = T, a.B = B, a.A = A, a.mode = mode;
     a.gamma = gamma, a.rho_bar = rho_bar, a.c_bar = c_bar;
     a.v_loss_c = v_loss_c, a.policy_loss_c = policy_loss_c, a.entropy_c = entropy_c;

@@ -14,7 +14,11 @@ include/impala_b200.h (PyTorch only provides device memory, streams and
 
 With `use_graph=True` the launch sequence between ingest and the (optional)
 collective, and the optimizer launch after it, are captured once into CUDA graphs and
-replayed each step.
+replayed each step.  Ingest is double buffered: two pinned host slabs, two device slabs and
+a dedicated copy stream, so the DMA of batch i+1 runs under the kernels of batch i
+(`ingest(slot)` / `step(slot)` order themselves with events); the loss scalars come back
+through a small ring of pinned buffers (`post_scalars` / `fetch_scalars`) so the host only
+ever waits for the previous step.
 """
 from __future__ import annotations
 
@@ -40,7 +44,7 @@ class LearnerEngine:
     def __init__(self, T: int, B_local: int, O: int, A: int, H_pi: int, H_v: int, hp,
                  global_batch: int | None = None, device: str | torch.device = "cuda:0",
                  mode: str = "reference", process_group=None, use_graph: bool = True,
-                 host_slabs: int = 2):
+                 slabs: int = 2):
         if not torch.cuda.is_available():
             raise _cabi.ImpalaCudaError("LearnerEngine needs a CUDA device; there is no CPU path")
         self.lib = _cabi.lib()
@@ -59,6 +63,7 @@ class LearnerEngine:
         self.inv_batch = 1.0 / self.global_batch
         self.use_graph = use_graph
         self.stream = torch.cuda.Stream(device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.launches_per_step = 0
 
         # ---- parameter blocks: [policy | value_fn], float32, 128-byte aligned tensors
@@ -76,25 +81,29 @@ class LearnerEngine:
 
         # ---- batch slab (device) and pinned staging slabs (host), identical layouts
         self.slab_off, self.slab_bytes = _cabi.batch_layout(T, B_local, O, A)
-        self.d_slab = torch.zeros(self.slab_bytes, dtype=torch.uint8, device=self.dev)
+        self.n_slabs = slabs
+        self.d_slabs = [torch.zeros(self.slab_bytes, dtype=torch.uint8, device=self.dev)
+                        for _ in range(slabs)]
         self.h_slabs = [torch.zeros(self.slab_bytes, dtype=torch.uint8).pin_memory()
-                        for _ in range(host_slabs)]
+                        for _ in range(slabs)]
         shapes = {"obs": (T + 1, B_local, O), "beh_logits": (T, B_local, A),
                   "actions": (T, B_local), "rewards": (T, B_local), "done": (T, B_local),
                   "lens": (B_local,)}
         self.shapes = shapes
-        self.d = {}
-        for (name, dt), off in zip(_BATCH_FIELDS, self.slab_off):
-            n = int(np.prod(shapes[name])) * np.dtype(dt).itemsize
-            self.d[name] = self.d_slab[off:off + n].view(_TORCH_DT[dt]).view(shapes[name])
-        self.h_views = []
-        for slab in self.h_slabs:
-            arr = slab.numpy()
-            views = {}
+        self.d_views, self.h_views = [], []
+        for dslab, hslab in zip(self.d_slabs, self.h_slabs):
+            arr = hslab.numpy()
+            dv, hv = {}, {}
             for (name, dt), off in zip(_BATCH_FIELDS, self.slab_off):
                 n = int(np.prod(shapes[name])) * np.dtype(dt).itemsize
-                views[name] = arr[off:off + n].view(dt).reshape(shapes[name])
-            self.h_views.append(views)
+                dv[name] = dslab[off:off + n].view(_TORCH_DT[dt]).view(shapes[name])
+                hv[name] = arr[off:off + n].view(dt).reshape(shapes[name])
+            self.d_views.append(dv)
+            self.h_views.append(hv)
+        self.d = self.d_views[0]
+        self.slab_ready = [torch.cuda.Event() for _ in range(slabs)]  # H2D into slab done
+        self.slab_free = [torch.cuda.Event() for _ in range(slabs)]   # last consumer of slab done
+        self._slab_used = [False] * slabs
 
         # ---- activations / gradients of the non-MLP part
         self.logits = torch.zeros(T, B_local, A, **f32)
@@ -108,9 +117,13 @@ class LearnerEngine:
         self.ws_vf_bytes = self._ws_bytes(self.M_vf, O, H_v, 1)
         self.ws_pi = torch.zeros(self.ws_pi_bytes, dtype=torch.uint8, device=self.dev)
         self.ws_vf = torch.zeros(self.ws_vf_bytes, dtype=torch.uint8, device=self.dev)
-        self.h_scalars = torch.zeros(8, dtype=torch.float64).pin_memory()
+        self.ws_vt_bytes = int(self.lib.impala_vtrace_loss_workspace(T, B_local, A))
+        self.ws_vt = torch.zeros(self.ws_vt_bytes, dtype=torch.uint8, device=self.dev)  # zeroed once
+        self.h_scalars = torch.zeros(4, 8, dtype=torch.float64).pin_memory()  # ring of 4 tickets
+        self._scalar_events = [torch.cuda.Event() for _ in range(4)]
+        self._ticket = 0
 
-        self._graph_main = None
+        self._graph_main = [None] * slabs
         self._graph_opt = None
         self.steps_done = 0
 
@@ -173,34 +186,42 @@ class LearnerEngine:
             np.copyto(self.h_views[slot][name], batch[name])
 
     def ingest(self, slot: int = 0) -> None:
-        _cabi.check(self.lib.impala_ingest(_ptr(self.d_slab), C.c_void_p(self.h_slabs[slot].data_ptr()),
-                                           self.slab_bytes, C.c_void_p(self.stream.cuda_stream)),
+        """Async H2D of pinned slab `slot` into device slab `slot` on the copy stream."""
+        cs = self.copy_stream
+        if self._slab_used[slot]:
+            cs.wait_event(self.slab_free[slot])  # the step that last read this slab is done
+        _cabi.check(self.lib.impala_ingest(_ptr(self.d_slabs[slot]),
+                                           C.c_void_p(self.h_slabs[slot].data_ptr()),
+                                           self.slab_bytes, C.c_void_p(cs.cuda_stream)),
                     "impala_ingest")
+        self.slab_ready[slot].record(cs)
 
-    def load_device_batch(self, batch: dict) -> None:
-        """Convenience for kernel-only timing: put a batch in HBM without the staging slab."""
-        self.fill_host(batch, 0)
-        self.ingest(0)
-        self.stream.synchronize()
+    def load_device_batch(self, batch: dict, slot: int = 0) -> None:
+        """Convenience for kernel-only timing: put a batch in HBM and wait for it."""
+        self.fill_host(batch, slot)
+        self.ingest(slot)
+        self.copy_stream.synchronize()
 
     # ------------------------------------------------------------------------ step
-    def _enqueue_main(self) -> int:
+    def _enqueue_main(self, slot: int = 0) -> int:
         lib, hp, st = self.lib, self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        d = self.d_views[slot]
         T, B, O, A = self.T, self.B, self.O, self.A
         p_pi = C.c_void_p(self.params.data_ptr())
         p_vf = C.c_void_p(self.params.data_ptr() + 4 * self.n_pi)
         g_pi = C.c_void_p(self.comm.data_ptr())
         g_vf = C.c_void_p(self.comm.data_ptr() + 8 * self.n_pi)
         scal = C.c_void_p(self.comm.data_ptr() + 8 * self.n_total)
-        obs = _ptr(self.d["obs"])
+        obs = _ptr(d["obs"])
         _cabi.check(lib.impala_mlp_forward(obs, p_pi, _ptr(self.logits), self.M_pi, O, self.H_pi, A, st),
                     "impala_mlp_forward(policy)")
         _cabi.check(lib.impala_mlp_forward(obs, p_vf, _ptr(self.values), self.M_vf, O, self.H_v, 1, st),
                     "impala_mlp_forward(value_fn)")
         _cabi.check(lib.impala_vtrace_loss(
-            _ptr(self.logits), _ptr(self.d["beh_logits"]), _ptr(self.d["actions"]),
-            _ptr(self.d["rewards"]), _ptr(self.d["done"]), _ptr(self.d["lens"]), _ptr(self.values),
-            _ptr(self.vs), _ptr(self.pg_adv), _ptr(self.dlogits), _ptr(self.dv), scal, T, B, A,
+            _ptr(self.logits), _ptr(d["beh_logits"]), _ptr(d["actions"]),
+            _ptr(d["rewards"]), _ptr(d["done"]), _ptr(d["lens"]), _ptr(self.values),
+            _ptr(self.vs), _ptr(self.pg_adv), _ptr(self.dlogits), _ptr(self.dv), scal,
+            _ptr(self.ws_vt), self.ws_vt_bytes, T, B, A,
             float(hp.gamma), float(hp.rho_bar), float(hp.c_bar), float(hp.v_loss_c),
             float(hp.policy_loss_c), float(hp.entropy_c), float(self.inv_batch), self.mode, st),
             "impala_vtrace_loss")
@@ -221,26 +242,31 @@ class LearnerEngine:
             0.9, 0.999, 1e-8, _ptr(self.norms), st), "impala_clip_adam")
         return 1
 
-    def _capture(self):
+    def _capture(self, slot: int):
         with torch.cuda.stream(self.stream):
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, stream=self.stream):
-                self._enqueue_main()
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, stream=self.stream):
-                self._enqueue_opt()
-        self._graph_main, self._graph_opt = g1, g2
+                self._enqueue_main(slot)
+            self._graph_main[slot] = g1
+            if self._graph_opt is None:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=self.stream):
+                    self._enqueue_opt()
+                self._graph_opt = g2
 
-    def step(self) -> None:
-        """One learner update on the batch currently in the device slab (async)."""
+    def step(self, slot: int = 0) -> None:
+        """One learner update on the batch in device slab `slot` (async on `self.stream`)."""
         with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.slab_ready[slot])
             if self.use_graph and self.steps_done >= 1:
-                if self._graph_main is None:
-                    self._capture()
-                self._graph_main.replay()
+                if self._graph_main[slot] is None:
+                    self._capture(slot)
+                self._graph_main[slot].replay()
                 n = 7
             else:
-                n = self._enqueue_main()  # first step eager: fills the launch-config caches
+                n = self._enqueue_main(slot)  # first step eager: fills the launch-config caches
+            self.slab_free[slot].record(self.stream)
+            self._slab_used[slot] = True
             if self.world > 1:
                 import torch.distributed as dist
 
@@ -256,15 +282,26 @@ class LearnerEngine:
     def forward_backward_only(self) -> None:
         """Everything up to (not including) the collective and the optimizer - for tests."""
         with torch.cuda.stream(self.stream):
-            self._enqueue_main()
+            self.stream.wait_event(self.slab_ready[0])
+            self._enqueue_main(0)
 
     def read_scalars(self) -> dict:
-        """D2H of the step's logged numbers (learner.py:217-240); synchronises the stream."""
+        """D2H of the step's logged numbers (learner.py:217-240); waits for the step."""
+        return self.fetch_scalars(self.post_scalars())
+
+    def post_scalars(self) -> int:
+        """Enqueue the D2H of the current step's scalars; returns a ticket for fetch_scalars."""
+        k = self._ticket % 4
+        self._ticket += 1
         with torch.cuda.stream(self.stream):
-            self.h_scalars[:4].copy_(self.comm[self.n_total:self.n_total + 4], non_blocking=True)
-            self.h_scalars[4:6].copy_(self.norms, non_blocking=True)
-        self.stream.synchronize()
-        s = self.h_scalars.tolist()
+            self.h_scalars[k, :4].copy_(self.comm[self.n_total:self.n_total + 4], non_blocking=True)
+            self.h_scalars[k, 4:6].copy_(self.norms, non_blocking=True)
+            self._scalar_events[k].record(self.stream)
+        return k
+
+    def fetch_scalars(self, ticket: int) -> dict:
+        self._scalar_events[ticket].synchronize()
+        s = self.h_scalars[ticket].tolist()
         hp = self.hp
         out = dict(zip(SCALAR_NAMES, s[:4]))
         out["total_loss"] = (hp.v_loss_c * out["value_fn_loss"] + hp.policy_loss_c * out["policy_loss"]
@@ -273,4 +310,5 @@ class LearnerEngine:
         return out
 
     def synchronize(self) -> None:
+        self.copy_stream.synchronize()
         self.stream.synchronize()

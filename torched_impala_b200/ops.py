@@ -99,9 +99,13 @@ def vtrace_loss(cur_logits, beh_logits, actions, rewards, done, lens, v, hp, inv
     dlogits = torch.empty(T, B, A, dtype=torch.float32, device=dev)
     dv = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
     scalars = torch.empty(4, dtype=torch.float64, device=dev)
-    _cabi.check(_cabi.lib().impala_vtrace_loss(
+    lib = _cabi.lib()
+    ws_bytes = int(lib.impala_vtrace_loss_workspace(T, B, A))
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    _cabi.check(lib.impala_vtrace_loss(
         _p(cur_logits), _p(beh_logits), _p(actions), _p(rewards), _p(done), _p(lens), _p(v), _p(vs),
-        _p(pg), _p(dlogits), _p(dv), _p(scalars), T, B, A, float(hp.gamma), float(hp.rho_bar),
+        _p(pg), _p(dlogits), _p(dv), _p(scalars), _p(ws), ws_bytes, T, B, A, float(hp.gamma),
+        float(hp.rho_bar),
         float(hp.c_bar), float(hp.v_loss_c), float(hp.policy_loss_c), float(hp.entropy_c),
         float(inv_batch), _cabi.MODES[mode], _st()), "impala_vtrace_loss")
     return dict(vs=vs, pg_adv=pg, dlogits=dlogits, dv=dv, scalars=scalars)
