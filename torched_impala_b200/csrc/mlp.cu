@@ -15,6 +15,7 @@
 //
 // This file: host-side configuration, occupancy cache, the partial reduction and the
 // C-ABI entry points.  Kernel templates: mlp_kernels.cuh; instantiations: mlp_inst.cu.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -147,6 +148,10 @@ int impala_mlp_launch(void (*kernel)(MlpArgs), const MlpArgs& a, const MlpConfig
 extern "C" int impala_mlp_forward(const float* x, const float* params, float* out, int M, int O,
                                   int H, int N2, void* stream) {
     if (!x || !params || !out) return IMPALA_ERR_BAD_ARG;
+    // GEMM-shaped layers go to the tensor cores (IMPALA_MLP_TC=0 forces the FP32 kernels).
+    const char* tc_env = std::getenv("IMPALA_MLP_TC");
+    if (!(tc_env && tc_env[0] == '0') && impala_mlp_fwd_tc_eligible(x, M, O, H, N2))
+        return impala_mlp_fwd_tc(x, params, out, M, O, H, N2, (cudaStream_t)stream);
     MlpArgs a{};
     MlpConfig c{};
     size_t smem;

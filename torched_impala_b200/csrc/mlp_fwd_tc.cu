@@ -1,0 +1,263 @@
+// MLP forward on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated 3xTF32.
+//
+//   out[m,:] = relu(x[m,:] W1^T + b1) W2^T + b2          (models.py:23-25 / :51-52, eval mode)
+//
+// Layer 1 is the GEMM: per 128-row tile  D[128, H] = X'[128, K'] * W1'[H, K']^T  with the bias
+// folded into K (X' = [x | 1 | 0..], W1' = [W1 | b1 | 0..], K' = 32 = one 128-byte swizzle row).
+// To stay within 1e-5 of the float64 reference, every fp32 operand is split into a tf32 "hi"
+// (round-to-nearest) and a "lo" remainder and three UMMAs are accumulated per K step:
+// hi*hi + lo*hi + hi*lo (the dropped lo*lo term is ~2^-22 relative).  Accumulators live in
+// TMEM (2 stages x 256 columns), so the CUDA cores only see the H hidden activations of a row
+// once: the epilogue thread that owns TMEM lane r applies ReLU and the tiny second layer
+// (<= 4 outputs) in registers and writes the row of logits / the value.
+//
+// Warp roles (288 threads, one persistent CTA per SM):
+//   warps 0-3  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast) -> global
+//   warps 4-7  producer: global x rows -> hi/lo split -> 128B-swizzled K-major smem tiles
+//   warp  8    TMEM allocator + single-thread UMMA issuer
+// Pipelines: smem stage full/empty mbarriers (producer <-> UMMA, freed by tcgen05.commit) and
+// TMEM stage full/empty mbarriers (UMMA <-> epilogue).
+#include "mlp_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kKPad = 32;     // floats per operand row = 128 bytes
+constexpr int kStages = 2;    // x tile stages in shared memory
+constexpr int kAccCols = 256; // TMEM columns per accumulator stage
+constexpr int kThreads = 9 * 32;
+constexpr int kTileBytes = kTileM * kKPad * 4;  // 16 KiB
+
+struct FwdTcArgs {
+    const float* x;
+    const float* params;
+    float* out;
+    int M, O, H, N2, num_tiles;
+    MlpLayout lay;
+};
+
+struct __align__(8) Barriers {
+    uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    // carve-up (all tile bases 1024-byte aligned for SWIZZLE_128B)
+    uint8_t* w_hi = smem;                                   // [H rows][128 B]  (<= 32 KiB)
+    uint8_t* w_lo = w_hi + 256 * 128;
+    uint8_t* x_hi = w_lo + 256 * 128;                       // kStages tiles
+    uint8_t* x_lo = x_hi + kStages * kTileBytes;
+    float* w2s = reinterpret_cast<float*>(x_lo + kStages * kTileBytes);  // [H][NP]
+    Barriers* bars = reinterpret_cast<Barriers*>(w2s + 256 * NP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* __restrict__ W1 = a.params + a.lay.oW1;
+    const float* __restrict__ b1 = a.params + a.lay.ob1;
+    const float* __restrict__ W2 = a.params + a.lay.oW2;
+    const float* __restrict__ b2 = a.params + a.lay.ob2;
+    const int O = a.O, H = a.H, ochunks = O >> 2;
+
+    // ---- one-time setup: W1' = [W1 | b1 | 0] split into hi/lo swizzled tiles, W2 transposed
+    for (int idx = tid; idx < H * 8; idx += kThreads) {
+        const int j = idx >> 3, c = idx & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ochunks) v = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
+        else if (c == ochunks) v.x = __ldg(b1 + j);
+        float4 hi, lo;
+        tc::split_tf32(v.x, hi.x, lo.x);
+        tc::split_tf32(v.y, hi.y, lo.y);
+        tc::split_tf32(v.z, hi.z, lo.z);
+        tc::split_tf32(v.w, hi.w, lo.w);
+        const uint32_t off = tc::sw128_offset(j, c);
+        *reinterpret_cast<float4*>(w_hi + off) = hi;
+        *reinterpret_cast<float4*>(w_lo + off) = lo;
+    }
+    for (int idx = tid; idx < H * NP; idx += kThreads) {
+        const int j = idx / NP, n = idx - j * NP;
+        w2s[idx] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
+    }
+    tc::fence_proxy_async();
+    if (warp == 8) {
+        tc::tmem_alloc(&bars->tmem_base, 512);
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                tc::mbar_init(&bars->full[s], 4 * 32);  // every producer thread arrives
+                tc::mbar_init(&bars->empty[s], 1);      // tcgen05.commit
+            }
+            for (int s = 0; s < 2; ++s) {
+                tc::mbar_init(&bars->acc_full[s], 1);        // tcgen05.commit
+                tc::mbar_init(&bars->acc_empty[s], 4 * 32);  // every epilogue thread arrives
+            }
+            tc::mbar_fence_init();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp < 4) {
+        // =============================== epilogue ===============================
+        float b2r[NP];
+#pragma unroll
+        for (int n = 0; n < NP; ++n) b2r[n] = n < a.N2 ? __ldg(b2 + n) : 0.f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1, aph = (it >> 1) & 1;
+            tc::mbar_wait(&bars->acc_full[as], aph);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + as * kAccCols;
+            float acc0[NP], acc1[NP];
+#pragma unroll
+            for (int n = 0; n < NP; ++n) acc0[n] = b2r[n], acc1[n] = 0.f;
+            for (int cb = 0; cb < H; cb += 32) {
+                float v[32];
+                tc::tmem_ld32(taddr + cb, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float h0 = fmaxf(v[i], 0.f), h1 = fmaxf(v[i + 1], 0.f);
+                    if constexpr (NP == 4) {
+                        const float4 wa = *reinterpret_cast<const float4*>(w2s + (cb + i) * 4);
+                        const float4 wb = *reinterpret_cast<const float4*>(w2s + (cb + i + 1) * 4);
+                        acc0[0] = fmaf(h0, wa.x, acc0[0]), acc0[1] = fmaf(h0, wa.y, acc0[1]);
+                        acc0[2] = fmaf(h0, wa.z, acc0[2]), acc0[3] = fmaf(h0, wa.w, acc0[3]);
+                        acc1[0] = fmaf(h1, wb.x, acc1[0]), acc1[1] = fmaf(h1, wb.y, acc1[1]);
+                        acc1[2] = fmaf(h1, wb.z, acc1[2]), acc1[3] = fmaf(h1, wb.w, acc1[3]);
+                    } else {
+                        const float2 w = *reinterpret_cast<const float2*>(w2s + cb + i);
+                        acc0[0] = fmaf(h0, w.x, acc0[0]);
+                        acc1[0] = fmaf(h1, w.y, acc1[0]);
+                    }
+                }
+            }
+            // all of this thread's TMEM reads are complete (wait::ld): release the stage
+            tc::tc_fence_before();
+            tc::mbar_arrive(&bars->acc_empty[as]);
+            const int row = tile * kTileM + 32 * warp + lane;
+            if (row < a.M) {
+                if (NP == 4 && a.N2 == 4) {
+                    *reinterpret_cast<float4*>(a.out + (size_t)row * 4) =
+                        make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2],
+                                    acc0[3] + acc1[3]);
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NP; ++n)
+                        if (n < a.N2) a.out[(size_t)row * a.N2 + n] = acc0[n] + acc1[n];
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =============================== producer ===============================
+        const int r = 32 * (warp - 4) + lane;  // row of the tile this thread fills
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStages, ph = (it / kStages) & 1;
+            const int row = tile * kTileM + r;
+            const bool valid = row < a.M;
+            float4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && c < ochunks)
+                    v[c] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)row * O) + c);
+                else if (c == ochunks)
+                    v[c].x = 1.f;  // the column that multiplies b1
+            }
+            tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMAs that read this stage have retired
+            uint8_t* th = x_hi + s * kTileBytes;
+            uint8_t* tl = x_lo + s * kTileBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 hi, lo;
+                tc::split_tf32(v[c].x, hi.x, lo.x);
+                tc::split_tf32(v[c].y, hi.y, lo.y);
+                tc::split_tf32(v[c].z, hi.z, lo.z);
+                tc::split_tf32(v[c].w, hi.w, lo.w);
+                const uint32_t off = tc::sw128_offset(r, c);
+                *reinterpret_cast<float4*>(th + off) = hi;
+                *reinterpret_cast<float4*>(tl + off) = lo;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&bars->full[s]);
+        }
+    } else {
+        // =============================== UMMA issuer ===============================
+        const uint32_t idesc = tc::instr_desc_tf32_m128(static_cast<uint32_t>(H));
+        const int ksteps = (O + 1 + 7) >> 3;  // K' = O data columns + the bias column
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStages, ph = (it / kStages) & 1;
+            const int as = it & 1, aph = (it >> 1) & 1;
+            tc::mbar_wait(&bars->full[s], ph);
+            tc::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+            tc::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t d = tmem_base + as * kAccCols;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes per K step
+                    const uint64_t a_hi = tc::smem_desc_k_sw128(x_hi + s * kTileBytes, ko);
+                    const uint64_t a_lo = tc::smem_desc_k_sw128(x_lo + s * kTileBytes, ko);
+                    const uint64_t b_hi = tc::smem_desc_k_sw128(w_hi, ko);
+                    const uint64_t b_lo = tc::smem_desc_k_sw128(w_lo, ko);
+                    tc::umma_tf32(d, a_hi, b_hi, idesc, kk > 0);
+                    tc::umma_tf32(d, a_lo, b_hi, idesc, true);
+                    tc::umma_tf32(d, a_hi, b_lo, idesc, true);
+                }
+                tc::umma_commit(&bars->empty[s]);      // smem stage reusable once the UMMAs retire
+                tc::umma_commit(&bars->acc_full[as]);  // accumulator ready for the epilogue
+            }
+            __syncwarp();
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * 256 * 128 + 2 * kStages * kTileBytes +
+                              256 * 4 * sizeof(float) + sizeof(Barriers);
+
+}  // namespace
+
+// Shapes the tensor-core path covers; everything else stays on the FP32 kernels.
+bool impala_mlp_fwd_tc_eligible(const float* x, int M, int O, int H, int N2) {
+    return M >= 1 && O >= 4 && O <= 28 && (O & 3) == 0 && H >= 16 && H <= 256 && (H & 31) == 0 &&
+           N2 >= 1 && N2 <= 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, int O, int H, int N2,
+                      cudaStream_t st) {
+    FwdTcArgs a{};
+    a.x = x, a.params = params, a.out = out;
+    a.M = M, a.O = O, a.H = H, a.N2 = N2;
+    a.num_tiles = (M + kTileM - 1) / kTileM;
+    a.lay = impala_make_layout(O, H, N2);
+    static int sms = 0;
+    static bool opted[2] = {false, false};
+    cudaError_t e;
+    if (!sms) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return (int)e;
+    }
+    const int which = N2 == 1 ? 0 : 1;
+    auto kernel = which ? mlp_fwd_tc_kernel<4> : mlp_fwd_tc_kernel<1>;
+    if (!opted[which]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        opted[which] = true;
+    }
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+    return impala_launch_status();
+}

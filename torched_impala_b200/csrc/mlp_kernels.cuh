@@ -29,6 +29,11 @@ constexpr int kMaxParts = 1024;  // upper bound on persistent CTAs (= per-CTA pa
 int impala_mlp_launch(void (*kernel)(MlpArgs), const MlpArgs& a, const MlpConfig& c, size_t smem,
                       cudaStream_t st, int* grid_out);
 
+// Tensor-core (tcgen05, 3xTF32) forward for GEMM-shaped layers, defined in mlp_fwd_tc.cu.
+bool impala_mlp_fwd_tc_eligible(const float* x, int M, int O, int H, int N2);
+int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, int O, int H, int N2,
+                      cudaStream_t st);
+
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \
     int impala_mlp_fwd_op##OPV(const MlpArgs&, const MlpConfig&, size_t, cudaStream_t, int*); \
