@@ -44,12 +44,15 @@ MLP_SHAPES = [
     # (M, O, H, N2)
     (21 * 8, 4, 32, 2), (21 * 8, 4, 32, 1), (1000, 7, 40, 3), (1000, 7, 24, 1),
     (20 * 64 + 5, 24, 256, 4), (21 * 64, 24, 256, 1), (333, 64, 512, 4), (333, 64, 512, 1),
-    (97, 32, 128, 16), (64, 8, 100, 5), (4097, 24, 256, 4),
+    (97, 32, 128, 16), (64, 8, 100, 5), (4097, 24, 256, 4), (86016, 24, 256, 1), (700, 28, 96, 3),
 ]
 
 
+@pytest.mark.parametrize("tensor_cores", ["1", "0"])
 @pytest.mark.parametrize("M,O,H,N2", MLP_SHAPES)
-def test_mlp_forward(ops, M, O, H, N2):
+def test_mlp_forward(ops, monkeypatch, M, O, H, N2, tensor_cores):
+    """Both forward paths: tcgen05 3xTF32 (default where the layer is GEMM-shaped) and FP32 FFMA."""
+    monkeypatch.setenv("IMPALA_MLP_TC", tensor_cores)
     rng = np.random.default_rng(M + O + H + N2)
     p = synth.init_params(M, O, N2, H)["policy"]
     x = rng.standard_normal((M, O), dtype=np.float32)

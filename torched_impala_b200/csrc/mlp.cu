@@ -181,7 +181,12 @@ extern "C" int impala_mlp_backward(const float* x, const float* params, const fl
         return IMPALA_ERR_WORKSPACE_TOO_SMALL;
     a.x = x, a.params = params, a.dout = dout, a.ws = (float*)workspace;
     int grid = 0;
-    int rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
+    int rc;
+    const char* tc_env = std::getenv("IMPALA_MLP_TC");
+    if (!(tc_env && tc_env[0] == '0') && impala_mlp_bwd_tc_eligible(x, dout, M, O, H, N2))
+        rc = impala_mlp_bwd_tc(x, params, dout, a.ws, M, O, H, N2, (cudaStream_t)stream, &grid);
+    else
+        rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
     if (rc != IMPALA_OK) return rc;
     const int64_t total = a.lay.total;
     reduce_partials_kernel<<<(unsigned)((total + 31) / 32), kRedWarps * 32, 0,

@@ -1,0 +1,372 @@
+// MLP backward on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated 3xTF32.
+//
+// Gradient of sum_m <dout[m,:], mlp(x[m,:])> w.r.t. (W1, b1, W2, b2)  (autograd at learner.py:175).
+// Transposed formulation so that a thread owns a HIDDEN unit (TMEM lane = hidden unit):
+//
+//   UMMA1 (recompute)  PRE[H, 32]  = W1'[H, K'] * X'[32, K']^T     X' = [x | 1 | 0], W1' = [W1 | b1 | 0]
+//   CUDA cores         h = relu(PRE);  dh = W2^T dz;  dW2 += dz h;  DP = (PRE > 0) ? dh : 0
+//   UMMA2 (reduction)  dW1'[H, K'] += DP[H, 32] * X'[32, K']        column O of dW1' is db1
+//
+// per tile of 32 batch rows.  K' = 32 floats = one 128-byte swizzle row, so the W1', DP and X'
+// tiles all share one shared-memory format (rows of 128 B, SWIZZLE_128B); the SAME X' bytes
+// serve as K-major B of UMMA1 and as MN-major B of UMMA2.  dW1' stays in TMEM for the whole
+// kernel (accumulated over every tile of the persistent CTA) and is read out once.  All
+// operands are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per
+// K step, which keeps the result within ~1e-6 relative of fp32.
+//
+// Warp roles (320 threads, one persistent CTA per SM):
+//   warps 0-7  epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
+//   warp  8    producer: TMA bulk copies of raw x / dout rows (8-deep ring) -> hi/lo swizzled tiles
+//   warp  9    TMEM allocator + single-thread UMMA issuer
+#include "mlp_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRowsT = 32;       // batch rows per tile: N of UMMA1, K of UMMA2
+constexpr int kXStages = 4;      // converted x / dz stages
+constexpr int kRawStages = 8;    // bulk-copy ring depth
+constexpr int kD1Stages = 4;     // TMEM stages of PRE
+constexpr int kThreads = 10 * 32;
+constexpr int kWTileBytes = 256 * 128;     // 256 hidden rows x 128 B
+constexpr int kXTileBytes = kRowsT * 128;  // 4 KiB
+constexpr int kRawStageBytes = 4096;       // x rows (<= 32*28*4 = 3584 B) | dout rows at +3584
+constexpr int kRawDzOffset = 3584;
+constexpr int kAccCol = 256;               // TMEM column of the dW1' accumulators
+
+struct BwdTcArgs {
+    const float* x;
+    const float* params;
+    const float* dout;
+    float* ws;
+    int M, O, H, N2, num_tiles;
+    MlpLayout lay;
+};
+
+struct __align__(8) Barriers {
+    uint64_t raw_full[kRawStages], full[kXStages], empty[kXStages];
+    uint64_t d1_full[kD1Stages], d1_empty[kD1Stages], dp_full, dp_free, done;
+    uint32_t tmem_base;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = w_hi + kWTileBytes;
+    uint8_t* dp_hi = w_lo + kWTileBytes;
+    uint8_t* dp_lo = dp_hi + kWTileBytes;
+    uint8_t* x_hi = dp_lo + kWTileBytes;              // kXStages tiles
+    uint8_t* x_lo = x_hi + kXStages * kXTileBytes;
+    uint8_t* raw = x_lo + kXStages * kXTileBytes;     // kRawStages x 4 KiB
+    float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][32][NP]
+    Barriers* bars = reinterpret_cast<Barriers*>(dzs + kXStages * kRowsT * NP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* __restrict__ W1 = a.params + a.lay.oW1;
+    const float* __restrict__ b1 = a.params + a.lay.ob1;
+    const float* __restrict__ W2 = a.params + a.lay.oW2;
+    const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
+    const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // ---- one-time setup
+    for (int idx = tid; idx < H * 8; idx += kThreads) {
+        const int j = idx >> 3, c = idx & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ochunks) v = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
+        else if (c == ochunks) v.x = __ldg(b1 + j);
+        float4 hi, lo;
+        tc::split_tf32(v.x, hi.x, lo.x);
+        tc::split_tf32(v.y, hi.y, lo.y);
+        tc::split_tf32(v.z, hi.z, lo.z);
+        tc::split_tf32(v.w, hi.w, lo.w);
+        const uint32_t off = tc::sw128_offset(j, c);
+        *reinterpret_cast<float4*>(w_hi + off) = hi;
+        *reinterpret_cast<float4*>(w_lo + off) = lo;
+    }
+    tc::fence_proxy_async();
+    if (warp == 9) {
+        tc::tmem_alloc(&bars->tmem_base, 512);
+        if (lane == 0) {
+            for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
+            for (int s = 0; s < kXStages; ++s) {
+                tc::mbar_init(&bars->full[s], 32);
+                tc::mbar_init(&bars->empty[s], 1);
+            }
+            for (int s = 0; s < kD1Stages; ++s) {
+                tc::mbar_init(&bars->d1_full[s], 1);
+                tc::mbar_init(&bars->d1_empty[s], nblk * 128);
+            }
+            tc::mbar_init(&bars->dp_full, nblk * 128);
+            tc::mbar_init(&bars->dp_free, 1);
+            tc::mbar_init(&bars->done, 1);
+            tc::mbar_fence_init();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp < 8) {
+        // =============================== epilogue ===============================
+        const int blk = warp >> 2, q = warp & 3, jl = 32 * q + lane, j = 128 * blk + jl;
+        float gb2 = 0.f;
+        if (blk < nblk) {
+            float w2r[NP], gw2[NP];
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                w2r[n] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
+                gw2[n] = 0.f;
+            }
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+            for (int i = 0; i < n_my; ++i) {
+                const int s = i % kXStages, ph = (i / kXStages) & 1;
+                const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
+                tc::mbar_wait(&bars->full[s], ph);      // dz rows of this tile are visible
+                tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
+                tc::tc_fence_after();
+                float v[32];
+                tc::tmem_ld32(lane_addr + d1 * 64 + blk * 32, v);
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars->d1_empty[d1]);
+                const float* dz_tile = dzs + s * kRowsT * NP;
+#pragma unroll
+                for (int r = 0; r < kRowsT; ++r) {
+                    float dz[NP];
+                    if constexpr (NP == 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(dz_tile + r * 4);
+                        dz[0] = t.x, dz[1] = t.y, dz[2] = t.z, dz[3] = t.w;
+                    } else {
+                        dz[0] = dz_tile[r];
+                    }
+                    const float pre = v[r], h = fmaxf(pre, 0.f);
+                    float dh = 0.f;
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) {
+                        dh = fmaf(dz[n], w2r[n], dh);
+                        gw2[n] = fmaf(dz[n], h, gw2[n]);
+                    }
+                    v[r] = pre > 0.f ? dh : 0.f;  // relu'(0) = 0 as in torch
+                }
+                if (tid < a.N2) {
+                    for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[r * NP + tid];
+                }
+                tc::mbar_wait(&bars->dp_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 hi, lo;
+                    tc::split_tf32(v[4 * c + 0], hi.x, lo.x);
+                    tc::split_tf32(v[4 * c + 1], hi.y, lo.y);
+                    tc::split_tf32(v[4 * c + 2], hi.z, lo.z);
+                    tc::split_tf32(v[4 * c + 3], hi.w, lo.w);
+                    const uint32_t off = blk * (128 * 128) + tc::sw128_offset(jl, c);
+                    *reinterpret_cast<float4*>(dp_hi + off) = hi;
+                    *reinterpret_cast<float4*>(dp_lo + off) = lo;
+                }
+                tc::fence_proxy_async();
+                tc::mbar_arrive(&bars->dp_full);
+            }
+            // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
+            tc::mbar_wait(&bars->done, 0);
+            tc::tc_fence_after();
+            float g[32];
+            tc::tmem_ld32(lane_addr + kAccCol + blk * 32, g);
+            float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < O) wsb[a.lay.oW1 + (size_t)j * O + k] = g[k];
+                else if (k == O) wsb[a.lay.ob1 + j] = g[k];
+            }
+#pragma unroll
+            for (int n = 0; n < NP; ++n)
+                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = gw2[n];
+            if (tid < a.N2) wsb[a.lay.ob2 + tid] = gb2;
+        }
+        // pads of the partial row (all 256 epilogue threads)
+        {
+            float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
+            const int64_t lo4[4] = {a.lay.oW1 + (int64_t)H * O, a.lay.ob1 + H,
+                                    a.lay.oW2 + (int64_t)a.N2 * H, a.lay.ob2 + a.N2};
+            const int64_t hi4[4] = {a.lay.ob1, a.lay.oW2, a.lay.ob2, a.lay.total};
+            for (int sgm = 0; sgm < 4; ++sgm)
+                for (int64_t p = lo4[sgm] + tid; p < hi4[sgm]; p += 256) wsb[p] = 0.f;
+        }
+    } else if (warp == 8) {
+        // =============================== producer ===============================
+        const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
+        auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+        auto is_full = [&](int i) { return (tile_of(i) + 1) * kRowsT <= a.M; };
+        auto issue_raw = [&](int i) {
+            if (lane == 0 && is_full(i)) {
+                const int rs = i % kRawStages;
+                uint8_t* dst = raw + rs * kRawStageBytes;
+                const size_t row0 = (size_t)tile_of(i) * kRowsT;
+                tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
+                tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes_x + bytes_z);
+                tc::bulk_g2s(dst, a.x + row0 * O, bytes_x, &bars->raw_full[rs]);
+                tc::bulk_g2s(dst + kRawDzOffset, a.dout + row0 * a.N2, bytes_z, &bars->raw_full[rs]);
+            }
+        };
+        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % kXStages, ph = (i / kXStages) & 1;
+            const int rs = i % kRawStages, rph = (i / kRawStages) & 1;
+            float4 v[8];
+            float z[NP];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NP; ++n) z[n] = 0.f;
+            if (is_full(i)) {
+                tc::mbar_wait(&bars->raw_full[rs], rph);
+                const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + lane * ochunks;
+                const float* rz = reinterpret_cast<const float*>(raw + rs * kRawStageBytes + kRawDzOffset) + lane * a.N2;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < ochunks) v[c] = rx[c];
+#pragma unroll
+                for (int n = 0; n < NP; ++n)
+                    if (n < a.N2) z[n] = rz[n];
+            } else {  // ragged last tile: plain guarded loads
+                const int row = tile_of(i) * kRowsT + lane;
+                if (row < a.M) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < ochunks) v[c] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)row * O) + c);
+#pragma unroll
+                    for (int n = 0; n < NP; ++n)
+                        if (n < a.N2) z[n] = __ldg(a.dout + (size_t)row * a.N2 + n);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1 / collects db1
+            __syncwarp();
+            if (i + kRawStages < n_my) issue_raw(i + kRawStages);  // refill the stage just drained
+            tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
+            uint8_t* th = x_hi + s * kXTileBytes;
+            uint8_t* tl = x_lo + s * kXTileBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 hi, lo;
+                tc::split_tf32(v[c].x, hi.x, lo.x);
+                tc::split_tf32(v[c].y, hi.y, lo.y);
+                tc::split_tf32(v[c].z, hi.z, lo.z);
+                tc::split_tf32(v[c].w, hi.w, lo.w);
+                const uint32_t off = tc::sw128_offset(lane, c);
+                *reinterpret_cast<float4*>(th + off) = hi;
+                *reinterpret_cast<float4*>(tl + off) = lo;
+            }
+#pragma unroll
+            for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + lane) * NP + n] = z[n];
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&bars->full[s]);
+        }
+    } else {
+        // =============================== UMMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT, false);
+            const uint32_t idesc2 = tc::instr_desc_tf32_m128(32, true);
+            const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
+            auto issue_umma1 = [&](int i) {
+                const int s = i % kXStages, ph = (i / kXStages) & 1;
+                const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
+                tc::mbar_wait(&bars->full[s], ph);
+                tc::mbar_wait(&bars->d1_empty[d1], dph ^ 1);
+                tc::tc_fence_after();
+                for (int b = 0; b < nblk; ++b) {
+                    const uint32_t d = tmem_base + d1 * 64 + b * 32;
+                    for (int kk = 0; kk < ksteps1; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        const uint64_t a_hi = tc::smem_desc_k_sw128(w_hi + b * (128 * 128), ko);
+                        const uint64_t a_lo = tc::smem_desc_k_sw128(w_lo + b * (128 * 128), ko);
+                        const uint64_t b_hi = tc::smem_desc_k_sw128(x_hi + s * kXTileBytes, ko);
+                        const uint64_t b_lo = tc::smem_desc_k_sw128(x_lo + s * kXTileBytes, ko);
+                        tc::umma_tf32(d, a_hi, b_hi, idesc1, kk > 0);
+                        tc::umma_tf32(d, a_lo, b_hi, idesc1, true);
+                        tc::umma_tf32(d, a_hi, b_lo, idesc1, true);
+                    }
+                }
+                tc::umma_commit(&bars->d1_full[d1]);
+            };
+            if (n_my > 0) issue_umma1(0);
+            if (n_my > 1) issue_umma1(1);
+            for (int i = 0; i < n_my; ++i) {
+                const int s = i % kXStages;
+                tc::mbar_wait(&bars->dp_full, i & 1);  // DP tiles of tile i are in shared memory
+                tc::tc_fence_after();
+                for (int b = 0; b < nblk; ++b) {
+                    const uint32_t d = tmem_base + kAccCol + b * 32;
+                    for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 32 batch rows, 8 per step
+                        const uint64_t a_hi = tc::smem_desc_k_sw128(dp_hi + b * (128 * 128), kk * 32);
+                        const uint64_t a_lo = tc::smem_desc_k_sw128(dp_lo + b * (128 * 128), kk * 32);
+                        const uint64_t b_hi = tc::smem_desc_mn_sw128(x_hi + s * kXTileBytes, kk);
+                        const uint64_t b_lo = tc::smem_desc_mn_sw128(x_lo + s * kXTileBytes, kk);
+                        tc::umma_tf32(d, a_hi, b_hi, idesc2, i > 0 || kk > 0);
+                        tc::umma_tf32(d, a_lo, b_hi, idesc2, true);
+                        tc::umma_tf32(d, a_hi, b_lo, idesc2, true);
+                    }
+                }
+                tc::umma_commit(&bars->dp_free);   // DP tiles reusable
+                tc::umma_commit(&bars->empty[s]);  // x / dz stage reusable
+                if (i + 2 < n_my) issue_umma1(i + 2);
+            }
+            tc::umma_commit(&bars->done);
+        }
+        __syncwarp();
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr size_t kSmemBytes = 1024 + 4 * kWTileBytes + 2 * kXStages * kXTileBytes +
+                              kRawStages * kRawStageBytes + kXStages * kRowsT * 4 * sizeof(float) +
+                              sizeof(Barriers);
+
+}  // namespace
+
+bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O, int H, int N2) {
+    return M >= 1 && O >= 4 && O <= 28 && (O & 3) == 0 && (H == 128 || H == 256) && N2 >= 1 &&
+           N2 <= 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
+}
+
+// Writes per-CTA partial gradient rows into ws (same layout as the FP32 kernel) and returns the
+// number of rows in *grid_out; the caller reduces them.
+int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws, int M,
+                      int O, int H, int N2, cudaStream_t st, int* grid_out) {
+    BwdTcArgs a{};
+    a.x = x, a.params = params, a.dout = dout, a.ws = ws;
+    a.M = M, a.O = O, a.H = H, a.N2 = N2;
+    a.num_tiles = (M + kRowsT - 1) / kRowsT;
+    a.lay = impala_make_layout(O, H, N2);
+    static int sms = 0;
+    static bool opted[2] = {false, false};
+    cudaError_t e;
+    if (!sms) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return (int)e;
+    }
+    const int which = N2 == 1 ? 0 : 1;
+    auto kernel = which ? mlp_bwd_tc_kernel<4> : mlp_bwd_tc_kernel<1>;
+    if (!opted[which]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        opted[which] = true;
+    }
+    int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    if (grid > kMaxParts) grid = kMaxParts;
+    kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+    *grid_out = grid;
+    return impala_launch_status();
+}

@@ -34,6 +34,11 @@ bool impala_mlp_fwd_tc_eligible(const float* x, int M, int O, int H, int N2);
 int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, int O, int H, int N2,
                       cudaStream_t st);
 
+// Tensor-core backward (mlp_bwd_tc.cu): per-CTA partial rows into ws, *grid_out rows written.
+bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O, int H, int N2);
+int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws, int M,
+                      int O, int H, int N2, cudaStream_t st, int* grid_out);
+
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \
     int impala_mlp_fwd_op##OPV(const MlpArgs&, const MlpConfig&, size_t, cudaStream_t, int*); \

@@ -38,6 +38,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// producer side of a transaction barrier: one arrival + `bytes` expected from bulk copies
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy (no tensor map): `bytes` contiguous bytes global -> shared, completion counted on
+// `bar`.  src/dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -93,12 +109,25 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(const void* tile, uint32_t
     d |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n (multiple of 16, <= 256)
-__device__ __forceinline__ uint32_t instr_desc_tf32_m128(uint32_t n) {
+// MN-major operand over the SAME memory image: rows are K (8-row groups 1024 B apart), the 32
+// floats of a row are the MN extent.  `k_group` selects the 8-row group of this K=8 step.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(const void* tile, uint32_t k_group) {
+    const uint32_t addr = smem_u32(tile) + k_group * 1024u;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1024 >> 4) << 16;  // leading byte offset: next 32-float MN block (unused, N = 32)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset: next 8-row K group
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// kind::tf32, fp32 accumulate, A K-major, M = 128, N = n (multiple of 16, <= 256);
+// b_mn_major selects an MN-major B operand.
+__device__ __forceinline__ uint32_t instr_desc_tf32_m128(uint32_t n, bool b_mn_major = false) {
     return (1u << 4)      // c_format = F32
            | (2u << 7)    // a_format = TF32
            | (2u << 10)   // b_format = TF32
-           | ((n >> 3) << 17) | ((128u >> 4) << 24);
+           | (b_mn_major ? (1u << 16) : 0u) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
