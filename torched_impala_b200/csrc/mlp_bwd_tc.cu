@@ -7,16 +7,19 @@
 //   CUDA cores         h = relu(PRE);  dh = W2^T dz;  dW2 += dz h;  DP = (PRE > 0) ? dh : 0
 //   UMMA2 (reduction)  dW1'[H, K'] += DP[H, 32] * X'[32, K']        column O of dW1' is db1
 //
-// per tile of 32 batch rows.  K' = 32 floats = one 128-byte swizzle row, so the W1', DP and X'
-// tiles all share one shared-memory format (rows of 128 B, SWIZZLE_128B); the SAME X' bytes
-// serve as K-major B of UMMA1 and as MN-major B of UMMA2.  dW1' stays in TMEM for the whole
+// per tile of 32 batch rows.  K' = 32 floats = one 128-byte swizzle row, so the W1', DP, X' and
+// X'^T tiles all share one shared-memory format (K-major rows of 128 B, SWIZZLE_128B).  The
+// producer writes every x tile twice: row-major (B of UMMA1, K = features) and transposed
+// (B of UMMA2, K = batch rows) - tf32 MN-major operands would need the 32-byte-swizzle
+// format, a second layout for the same bytes, so the transpose is done once on the way into
+// shared memory instead.  dW1' stays in TMEM for the whole
 // kernel (accumulated over every tile of the persistent CTA) and is read out once.  All
 // operands are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per
 // K step, which keeps the result within ~1e-6 relative of fp32.
 //
 // Warp roles (320 threads, one persistent CTA per SM):
 //   warps 0-7  epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
-//   warp  8    producer: TMA bulk copies of raw x / dout rows (8-deep ring) -> hi/lo swizzled tiles
+//   warp  8    producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo swizzled tiles
 //   warp  9    TMEM allocator + single-thread UMMA issuer
 #include "mlp_kernels.cuh"
 #include "tc_common.cuh"
@@ -24,8 +27,9 @@
 namespace {
 
 constexpr int kRowsT = 32;       // batch rows per tile: N of UMMA1, K of UMMA2
-constexpr int kXStages = 4;      // converted x / dz stages
-constexpr int kRawStages = 8;    // bulk-copy ring depth
+constexpr int kKPad = 32;        // padded feature count K' (data + bias column + zeros)
+constexpr int kXStages = 3;      // converted x / x^T / dz stages
+constexpr int kRawStages = 4;    // bulk-copy ring depth
 constexpr int kD1Stages = 4;     // TMEM stages of PRE
 constexpr int kThreads = 10 * 32;
 constexpr int kWTileBytes = 256 * 128;     // 256 hidden rows x 128 B
@@ -60,7 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     uint8_t* dp_lo = dp_hi + kWTileBytes;
     uint8_t* x_hi = dp_lo + kWTileBytes;              // kXStages tiles
     uint8_t* x_lo = x_hi + kXStages * kXTileBytes;
-    uint8_t* raw = x_lo + kXStages * kXTileBytes;     // kRawStages x 4 KiB
+    uint8_t* xt_hi = x_lo + kXStages * kXTileBytes;   // transposed tiles: row = feature, col = batch row
+    uint8_t* xt_lo = xt_hi + kXStages * kXTileBytes;
+    uint8_t* raw = xt_lo + kXStages * kXTileBytes;    // kRawStages x 4 KiB
     float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][32][NP]
     Barriers* bars = reinterpret_cast<Barriers*>(dzs + kXStages * kRowsT * NP);
 
@@ -259,6 +265,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 const uint32_t off = tc::sw128_offset(lane, c);
                 *reinterpret_cast<float4*>(th + off) = hi;
                 *reinterpret_cast<float4*>(tl + off) = lo;
+                // transposed copy: element (feature 4c+e, batch row `lane`)
+                uint8_t* tth = xt_hi + s * kXTileBytes + (lane & 3) * 4;
+                uint8_t* ttl = xt_lo + s * kXTileBytes + (lane & 3) * 4;
+                const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t toff = tc::sw128_offset(4 * c + e, lane >> 2);
+                    *reinterpret_cast<float*>(tth + toff) = hv[e];
+                    *reinterpret_cast<float*>(ttl + toff) = lv[e];
+                }
             }
 #pragma unroll
             for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + lane) * NP + n] = z[n];
@@ -268,8 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     } else {
         // =============================== UMMA issuer ===============================
         if (lane == 0) {
-            const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT, false);
-            const uint32_t idesc2 = tc::instr_desc_tf32_m128(32, true);
+            const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 32 batch rows
+            const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);   // N = 32 feature columns
             const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
             auto issue_umma1 = [&](int i) {
                 const int s = i % kXStages, ph = (i / kXStages) & 1;
@@ -303,8 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                     for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 32 batch rows, 8 per step
                         const uint64_t a_hi = tc::smem_desc_k_sw128(dp_hi + b * (128 * 128), kk * 32);
                         const uint64_t a_lo = tc::smem_desc_k_sw128(dp_lo + b * (128 * 128), kk * 32);
-                        const uint64_t b_hi = tc::smem_desc_mn_sw128(x_hi + s * kXTileBytes, kk);
-                        const uint64_t b_lo = tc::smem_desc_mn_sw128(x_lo + s * kXTileBytes, kk);
+                        const uint64_t b_hi = tc::smem_desc_k_sw128(xt_hi + s * kXTileBytes, kk * 32);
+                        const uint64_t b_lo = tc::smem_desc_k_sw128(xt_lo + s * kXTileBytes, kk * 32);
                         tc::umma_tf32(d, a_hi, b_hi, idesc2, i > 0 || kk > 0);
                         tc::umma_tf32(d, a_lo, b_hi, idesc2, true);
                         tc::umma_tf32(d, a_hi, b_lo, idesc2, true);
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     }
 }
 
-constexpr size_t kSmemBytes = 1024 + 4 * kWTileBytes + 2 * kXStages * kXTileBytes +
+constexpr size_t kSmemBytes = 1024 + 4 * kWTileBytes + 4 * kXStages * kXTileBytes +
                               kRawStages * kRawStageBytes + kXStages * kRowsT * 4 * sizeof(float) +
                               sizeof(Barriers);
 

@@ -109,25 +109,14 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(const void* tile, uint32_t
     d |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
     return d;
 }
-// MN-major operand over the SAME memory image: rows are K (8-row groups 1024 B apart), the 32
-// floats of a row are the MN extent.  `k_group` selects the 8-row group of this K=8 step.
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(const void* tile, uint32_t k_group) {
-    const uint32_t addr = smem_u32(tile) + k_group * 1024u;
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);
-    d |= static_cast<uint64_t>(1024 >> 4) << 16;  // leading byte offset: next 32-float MN block (unused, N = 32)
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset: next 8-row K group
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-// kind::tf32, fp32 accumulate, A K-major, M = 128, N = n (multiple of 16, <= 256);
-// b_mn_major selects an MN-major B operand.
-__device__ __forceinline__ uint32_t instr_desc_tf32_m128(uint32_t n, bool b_mn_major = false) {
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n (multiple of 16, <= 256).
+// (tf32 MN-major operands exist but only in the SWIZZLE_128B_BASE32B format, a different memory
+// image from the K-major tiles used here - the kernels transpose on the way into smem instead.)
+__device__ __forceinline__ uint32_t instr_desc_tf32_m128(uint32_t n) {
     return (1u << 4)      // c_format = F32
            | (2u << 7)    // a_format = TF32
            | (2u << 10)   // b_format = TF32
-           | (b_mn_major ? (1u << 16) : 0u) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+           | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
