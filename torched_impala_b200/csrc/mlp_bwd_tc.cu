@@ -21,10 +21,26 @@
 //   warps 0-7  epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
 //   warp  8    producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo swizzled tiles
 //   warp  9    TMEM allocator + single-thread UMMA issuer
+#include <cstdlib>
+
 #include "mlp_kernels.cuh"
 #include "tc_common.cuh"
 
+// Debug timeline (IMPALA_TC_TRACE=1): CTA 0 records (event, tile, clock64) triples; read back
+// through impala_debug_read_trace (not part of the public ABI).
+__device__ long long g_trace[3 * 4096];
+__device__ int g_trace_n;
+
 namespace {
+
+__device__ __forceinline__ void trace(bool on, int ev, int tile) {
+    if (on) {
+        const int k = atomicAdd(&g_trace_n, 1);
+        if (k < 4096) {
+            g_trace[3 * k] = ev, g_trace[3 * k + 1] = tile, g_trace[3 * k + 2] = clock64();
+        }
+    }
+}
 
 constexpr int kRowsT = 32;       // batch rows per tile: N of UMMA1, K of UMMA2
 constexpr int kKPad = 32;        // padded feature count K' (data + bias column + zeros)
@@ -44,6 +60,7 @@ struct BwdTcArgs {
     const float* dout;
     float* ws;
     int M, O, H, N2, num_tiles;
+    int trace;
     MlpLayout lay;
 };
 
@@ -76,6 +93,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     const float* __restrict__ W2 = a.params + a.lay.oW2;
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
     const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp >= 8);
+    trace(tr && warp == 0, 0, -1);
 
     // ---- one-time setup
     for (int idx = tid; idx < H * 8; idx += kThreads) {
@@ -131,9 +150,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % kXStages, ph = (i / kXStages) & 1;
                 const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
+                trace(tr, 10, i);
                 tc::mbar_wait(&bars->full[s], ph);      // dz rows of this tile are visible
                 tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
+                trace(tr, 11, i);
                 float v[32];
                 tc::tmem_ld32(lane_addr + d1 * 64 + blk * 32, v);
                 tc::tc_fence_before();
@@ -160,7 +181,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 if (tid < a.N2) {
                     for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[r * NP + tid];
                 }
+                trace(tr, 12, i);
                 tc::mbar_wait(&bars->dp_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
+                trace(tr, 13, i);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 hi, lo;
@@ -174,10 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&bars->dp_full);
+                trace(tr, 14, i);
             }
             // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
             tc::mbar_wait(&bars->done, 0);
             tc::tc_fence_after();
+            trace(tr, 15, n_my);
             float g[32];
             tc::tmem_ld32(lane_addr + kAccCol + blk * 32, g);
             float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
@@ -226,8 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NP; ++n) z[n] = 0.f;
+            trace(tr, 20, i);
             if (is_full(i)) {
                 tc::mbar_wait(&bars->raw_full[rs], rph);
+                trace(tr, 21, i);
                 const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + lane * ochunks;
                 const float* rz = reinterpret_cast<const float*>(raw + rs * kRawStageBytes + kRawDzOffset) + lane * a.N2;
 #pragma unroll
@@ -252,7 +279,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1 / collects db1
             __syncwarp();
             if (i + kRawStages < n_my) issue_raw(i + kRawStages);  // refill the stage just drained
+            trace(tr, 22, i);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
+            trace(tr, 23, i);
             uint8_t* th = x_hi + s * kXTileBytes;
             uint8_t* tl = x_lo + s * kXTileBytes;
 #pragma unroll
@@ -280,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + lane) * NP + n] = z[n];
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
+            trace(tr, 24, i);
         }
     } else {
         // =============================== UMMA issuer ===============================
@@ -290,9 +320,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             auto issue_umma1 = [&](int i) {
                 const int s = i % kXStages, ph = (i / kXStages) & 1;
                 const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
+                trace(tr, 30, i);
                 tc::mbar_wait(&bars->full[s], ph);
                 tc::mbar_wait(&bars->d1_empty[d1], dph ^ 1);
                 tc::tc_fence_after();
+                trace(tr, 31, i);
                 for (int b = 0; b < nblk; ++b) {
                     const uint32_t d = tmem_base + d1 * 64 + b * 32;
                     for (int kk = 0; kk < ksteps1; ++kk) {
@@ -307,13 +339,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                     }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
+                trace(tr, 32, i);
             };
             if (n_my > 0) issue_umma1(0);
             if (n_my > 1) issue_umma1(1);
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % kXStages;
+                trace(tr, 33, i);
                 tc::mbar_wait(&bars->dp_full, i & 1);  // DP tiles of tile i are in shared memory
                 tc::tc_fence_after();
+                trace(tr, 34, i);
                 for (int b = 0; b < nblk; ++b) {
                     const uint32_t d = tmem_base + kAccCol + b * 32;
                     for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 32 batch rows, 8 per step
@@ -328,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 }
                 tc::umma_commit(&bars->dp_free);   // DP tiles reusable
                 tc::umma_commit(&bars->empty[s]);  // x / dz stage reusable
+                trace(tr, 35, i);
                 if (i + 2 < n_my) issue_umma1(i + 2);
             }
             tc::umma_commit(&bars->done);
@@ -364,6 +400,12 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
     a.num_tiles = (M + kRowsT - 1) / kRowsT;
     a.lay = impala_make_layout(O, H, N2);
+    const char* tr_env = std::getenv("IMPALA_TC_TRACE");
+    a.trace = tr_env && tr_env[0] == '1';
+    if (a.trace) {
+        const int zero = 0;
+        cudaMemcpyToSymbolAsync(g_trace_n, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+    }
     static int sms = 0;
     static bool opted[2] = {false, false};
     cudaError_t e;
@@ -385,4 +427,15 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     *grid_out = grid;
     return impala_launch_status();
+}
+
+// Debug only: copies up to n (event, tile, clock) triples of the last traced launch; returns count.
+extern "C" int impala_debug_read_trace(long long* out, int n) {
+    int cnt = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(&cnt, g_trace_n, sizeof(int)) != cudaSuccess) return -1;
+    if (cnt > 4096) cnt = 4096;
+    if (cnt > n) cnt = n;
+    if (cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * cnt) != cudaSuccess) return -1;
+    return cnt;
 }
