@@ -313,61 +313,70 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         }
     } else {
         // =============================== UMMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 32 batch rows
-            const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);   // N = 32 feature columns
-            const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
-            auto issue_umma1 = [&](int i) {
-                const int s = i % kXStages, ph = (i / kXStages) & 1;
-                const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
-                trace(tr, 30, i);
-                tc::mbar_wait(&bars->full[s], ph);
-                tc::mbar_wait(&bars->d1_empty[d1], dph ^ 1);
-                tc::tc_fence_after();
-                trace(tr, 31, i);
+        // The whole warp runs the schedule (warp-uniform descriptors stay in uniform registers);
+        // one elected lane issues the UMMAs and their commits.
+        const uint32_t idesc = tc::instr_desc_tf32_m128(kRowsT);  // N = 32 for both UMMAs
+        const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
+        const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
+        const uint64_t dp_hi_d = tc::smem_desc_k_sw128(dp_hi, 0), dp_lo_d = tc::smem_desc_k_sw128(dp_lo, 0);
+        const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
+        const uint64_t dxt_hi = tc::smem_desc_k_sw128(xt_hi, 0), dxt_lo = tc::smem_desc_k_sw128(xt_lo, 0);
+        constexpr uint64_t kBlkOff = (128 * 128) >> 4;  // next 128-row block of a 256-row tile
+        auto issue_umma1 = [&](int i) {
+            const int s = i % kXStages, ph = (i / kXStages) & 1;
+            const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
+            trace(tr, 30, i);
+            tc::mbar_wait(&bars->full[s], ph);
+            tc::mbar_wait(&bars->d1_empty[d1], dph ^ 1);
+            tc::tc_fence_after();
+            trace(tr, 31, i);
+            if (tc::elect_one()) {
+                const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
+#pragma unroll 1
                 for (int b = 0; b < nblk; ++b) {
                     const uint32_t d = tmem_base + d1 * 64 + b * 32;
+#pragma unroll 1
                     for (int kk = 0; kk < ksteps1; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        const uint64_t a_hi = tc::smem_desc_k_sw128(w_hi + b * (128 * 128), ko);
-                        const uint64_t a_lo = tc::smem_desc_k_sw128(w_lo + b * (128 * 128), ko);
-                        const uint64_t b_hi = tc::smem_desc_k_sw128(x_hi + s * kXTileBytes, ko);
-                        const uint64_t b_lo = tc::smem_desc_k_sw128(x_lo + s * kXTileBytes, ko);
-                        tc::umma_tf32(d, a_hi, b_hi, idesc1, kk > 0);
-                        tc::umma_tf32(d, a_lo, b_hi, idesc1, true);
-                        tc::umma_tf32(d, a_hi, b_lo, idesc1, true);
+                        const uint64_t ko = 2 * kk, bo = b * kBlkOff;
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_hi + so + ko, idesc, kk > 0);
+                        tc::umma_tf32(d, dw_lo + bo + ko, dx_hi + so + ko, idesc, true);
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_lo + so + ko, idesc, true);
                     }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
-                trace(tr, 32, i);
-            };
-            if (n_my > 0) issue_umma1(0);
-            if (n_my > 1) issue_umma1(1);
-            for (int i = 0; i < n_my; ++i) {
-                const int s = i % kXStages;
-                trace(tr, 33, i);
-                tc::mbar_wait(&bars->dp_full, i & 1);  // DP tiles of tile i are in shared memory
-                tc::tc_fence_after();
-                trace(tr, 34, i);
+            }
+            __syncwarp();
+            trace(tr, 32, i);
+        };
+        if (n_my > 0) issue_umma1(0);
+        if (n_my > 1) issue_umma1(1);
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % kXStages;
+            trace(tr, 33, i);
+            tc::mbar_wait(&bars->dp_full, i & 1);  // DP tiles of tile i are in shared memory
+            tc::tc_fence_after();
+            trace(tr, 34, i);
+            if (tc::elect_one()) {
+                const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
+#pragma unroll 1
                 for (int b = 0; b < nblk; ++b) {
                     const uint32_t d = tmem_base + kAccCol + b * 32;
+#pragma unroll 1
                     for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 32 batch rows, 8 per step
-                        const uint64_t a_hi = tc::smem_desc_k_sw128(dp_hi + b * (128 * 128), kk * 32);
-                        const uint64_t a_lo = tc::smem_desc_k_sw128(dp_lo + b * (128 * 128), kk * 32);
-                        const uint64_t b_hi = tc::smem_desc_k_sw128(xt_hi + s * kXTileBytes, kk * 32);
-                        const uint64_t b_lo = tc::smem_desc_k_sw128(xt_lo + s * kXTileBytes, kk * 32);
-                        tc::umma_tf32(d, a_hi, b_hi, idesc2, i > 0 || kk > 0);
-                        tc::umma_tf32(d, a_lo, b_hi, idesc2, true);
-                        tc::umma_tf32(d, a_hi, b_lo, idesc2, true);
+                        const uint64_t ko = 2 * kk, bo = b * kBlkOff;
+                        tc::umma_tf32(d, dp_hi_d + bo + ko, dxt_hi + so + ko, idesc, i > 0 || kk > 0);
+                        tc::umma_tf32(d, dp_lo_d + bo + ko, dxt_hi + so + ko, idesc, true);
+                        tc::umma_tf32(d, dp_hi_d + bo + ko, dxt_lo + so + ko, idesc, true);
                     }
                 }
                 tc::umma_commit(&bars->dp_free);   // DP tiles reusable
                 tc::umma_commit(&bars->empty[s]);  // x / dz stage reusable
-                trace(tr, 35, i);
-                if (i + 2 < n_my) issue_umma1(i + 2);
             }
-            tc::umma_commit(&bars->done);
+            __syncwarp();
+            trace(tr, 35, i);
+            if (i + 2 < n_my) issue_umma1(i + 2);
         }
+        if (tc::elect_one()) tc::umma_commit(&bars->done);
         __syncwarp();
     }
 

@@ -187,8 +187,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
         }
     } else {
         // =============================== UMMA issuer ===============================
+        // The whole warp runs the schedule (warp-uniform descriptors stay in uniform registers);
+        // one elected lane issues the UMMAs and their commits.
         const uint32_t idesc = tc::instr_desc_tf32_m128(static_cast<uint32_t>(H));
         const int ksteps = (O + 1 + 7) >> 3;  // K' = O data columns + the bias column
+        const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
+        const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
@@ -196,17 +200,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             tc::mbar_wait(&bars->full[s], ph);
             tc::mbar_wait(&bars->acc_empty[as], aph ^ 1);
             tc::tc_fence_after();
-            if (lane == 0) {
+            if (tc::elect_one()) {
                 const uint32_t d = tmem_base + as * kAccCols;
+                const uint64_t so = static_cast<uint64_t>((s * kTileBytes) >> 4);
+#pragma unroll 1
                 for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes per K step
-                    const uint64_t a_hi = tc::smem_desc_k_sw128(x_hi + s * kTileBytes, ko);
-                    const uint64_t a_lo = tc::smem_desc_k_sw128(x_lo + s * kTileBytes, ko);
-                    const uint64_t b_hi = tc::smem_desc_k_sw128(w_hi, ko);
-                    const uint64_t b_lo = tc::smem_desc_k_sw128(w_lo, ko);
-                    tc::umma_tf32(d, a_hi, b_hi, idesc, kk > 0);
-                    tc::umma_tf32(d, a_lo, b_hi, idesc, true);
-                    tc::umma_tf32(d, a_hi, b_lo, idesc, true);
+                    const uint64_t ko = 2 * kk;  // 32 bytes per K = 8 step, in 16-byte units
+                    tc::umma_tf32(d, dx_hi + so + ko, dw_hi + ko, idesc, kk > 0);
+                    tc::umma_tf32(d, dx_lo + so + ko, dw_hi + ko, idesc, true);
+                    tc::umma_tf32(d, dx_hi + so + ko, dw_lo + ko, idesc, true);
                 }
                 tc::umma_commit(&bars->empty[s]);      // smem stage reusable once the UMMAs retire
                 tc::umma_commit(&bars->acc_full[as]);  // accumulator ready for the epilogue
