@@ -1,0 +1,24 @@
+"""GPU (>= 2 devices): data-parallel learner over NCCL equals the single-GPU full-batch learner."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_rank_nccl_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), script],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MULTI_GPU_OK" in res.stdout
