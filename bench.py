@@ -422,6 +422,12 @@ def run_own_arm(args):
 
 
 def main():
+    # Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON
+    # line there.  Keep the real stdout aside, point fd 1 at stderr for the duration of the run
+    # and emit the JSON line through the saved descriptor.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -434,6 +440,7 @@ def main():
         run_reference_arm(args)
     else:
         run_own_arm(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -119,6 +119,21 @@ int impala_clip_adam(float* params, const double* grad, float* m, float* v, int6
                      int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
                      float beta2, float eps, double* norms_out, void* stream);
 
+/* Pieces of the reference's module-level loss helpers (learner.py:298-321) for callers that use
+ * them individually instead of impala_vtrace_loss.  logits (M,A) f32 row-major, actions (M) i32.
+ *   log_prob[m]    = log_softmax(logits[m])[actions[m]]           action_log_probs        (:298-303)
+ *   neg_entropy[m] = sum_k p_k log p_k                            compute_entropy_loss    (:310-314)
+ * backward: dlogits from the upstream gradients of the two outputs (either may be NULL = 0). */
+int impala_policy_terms(const float* logits, const int32_t* actions, float* log_prob,
+                        float* neg_entropy, int M, int A, void* stream);
+int impala_policy_terms_backward(const float* logits, const int32_t* actions,
+                                 const float* grad_log_prob, const float* grad_neg_entropy,
+                                 float* dlogits, int M, int A, void* stream);
+
+/* Float64 scalar reductions of f32 vectors: mode 0 = sum a, 1 = 0.5 sum a^2 (compute_baseline_loss,
+ * learner.py:306-307), 2 = sum a*b (the sum in compute_policy_gradient_loss, :317-321). */
+int impala_reduce(const float* a, const float* b, int64_t n, int mode, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

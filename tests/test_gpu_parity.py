@@ -266,3 +266,33 @@ def test_full_size_properties():
     assert np.abs(full - padded).max() < 1e-5 * scale
     halves = sum(run(T, synth.shard_batch(batch, r, 2), B // 2, B) for r in range(2))
     assert np.abs(full - halves).max() < 1e-5 * scale
+
+
+def test_loss_helper_functions_match_reference_formulas():
+    """The four module-level helpers of learner.py:298-321 (values and gradients), float64 torch on
+    the CPU as the reference of the formulas."""
+    import torch.nn.functional as F
+
+    from torched_impala_b200 import learner as L
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    torch.manual_seed(0)
+    Lr, A = 37, 5
+    z = torch.randn(Lr, A, dtype=torch.float64, requires_grad=True)
+    a = torch.randint(0, A, (Lr, 1))
+    adv = torch.randn(Lr, dtype=torch.float64)
+    lsm = F.log_softmax(z, -1)
+    ref = dict(alp=lsm.gather(-1, a), base=0.5 * (adv ** 2).sum(), ent=(lsm.exp() * lsm).sum(),
+               pg=(-lsm.gather(-1, a).view(-1) * adv).sum())
+    g_ref = torch.autograd.grad(ref["ent"] * 0.3 + ref["pg"] * 1.7 + ref["alp"].sum() * 0.5, z)[0]
+    zc = z.detach().cuda().requires_grad_(True)
+    ac, advc = a.cuda(), adv.cuda().requires_grad_(True)
+    got = dict(alp=L.action_log_probs(zc, ac), base=L.compute_baseline_loss(advc),
+               ent=L.compute_entropy_loss(zc), pg=L.compute_policy_gradient_loss(zc, ac, advc))
+    assert got["alp"].shape == a.shape and got["alp"].dtype == torch.float64
+    for k in ref:
+        assert (got[k].detach().cpu() - ref[k].detach()).abs().max() < 1e-5, k
+    (got["ent"] * 0.3 + got["pg"] * 1.7 + got["alp"].sum() * 0.5 + got["base"]).backward()
+    assert (zc.grad.cpu() - g_ref).abs().max() < 1e-5
+    assert (advc.grad.cpu() - adv).abs().max() < 1e-5  # d(0.5 sum adv^2) = adv; pg loss detaches adv

@@ -235,3 +235,109 @@ class Learner:
     @property
     def policy_weights(self):
         return self.policy.state_dict()
+
+
+# ----------------------------------------------------------------------------------------------
+# Module-level loss helpers with the reference's names, signatures and sign conventions
+# (learner.py:298-321), backed by the C ABI.  Inputs are CUDA tensors (any float dtype; the
+# kernels compute in float32 and reduce in float64); results come back in the input dtype and
+# are differentiable with respect to the logits / advantages exactly where the reference's are.
+# ----------------------------------------------------------------------------------------------
+def _lib_and_stream():
+    import ctypes as C
+
+    from . import _cabi
+
+    return _cabi, _cabi.lib(), C.c_void_p(torch.cuda.current_stream().cuda_stream), C
+
+
+def _cuda_f32(t):
+    from . import _cabi
+
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise _cabi.ImpalaCudaError("loss helpers need CUDA tensors (there is no CPU fallback)")
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _PolicyTerms(torch.autograd.Function):
+    """(logits, actions) -> (log pi(a), sum_k p_k log p_k) per row."""
+
+    @staticmethod
+    def forward(ctx, logits, actions):
+        _cabi, lib, st, C = _lib_and_stream()
+        z = _cuda_f32(logits).reshape(-1, logits.shape[-1])
+        a = actions.detach().reshape(-1).to(torch.int32).contiguous()
+        M, A = z.shape
+        lp = torch.empty(M, dtype=torch.float32, device=z.device)
+        ne = torch.empty(M, dtype=torch.float32, device=z.device)
+        _cabi.check(lib.impala_policy_terms(C.c_void_p(z.data_ptr()), C.c_void_p(a.data_ptr()),
+                                            C.c_void_p(lp.data_ptr()), C.c_void_p(ne.data_ptr()), M, A, st),
+                    "impala_policy_terms")
+        ctx.save_for_backward(z, a)
+        ctx.in_shape, ctx.in_dtype = logits.shape, logits.dtype
+        return lp.to(logits.dtype), ne.to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ne):
+        _cabi, lib, st, C = _lib_and_stream()
+        z, a = ctx.saved_tensors
+        M, A = z.shape
+        gl = None if g_lp is None else g_lp.to(torch.float32).contiguous()
+        gn = None if g_ne is None else g_ne.to(torch.float32).contiguous()
+        dz = torch.empty_like(z)
+        _cabi.check(lib.impala_policy_terms_backward(
+            C.c_void_p(z.data_ptr()), C.c_void_p(a.data_ptr()),
+            C.c_void_p(gl.data_ptr()) if gl is not None else None,
+            C.c_void_p(gn.data_ptr()) if gn is not None else None,
+            C.c_void_p(dz.data_ptr()), M, A, st), "impala_policy_terms_backward")
+        return dz.reshape(ctx.in_shape).to(ctx.in_dtype), None
+
+
+class _Reduce(torch.autograd.Function):
+    """float64-accumulated scalar reductions: mode 0 sum(a), 1 0.5*sum(a^2), 2 sum(a*b) (b constant)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode):
+        _cabi, lib, st, C = _lib_and_stream()
+        af = _cuda_f32(a).reshape(-1)
+        bf = _cuda_f32(b).reshape(-1) if b is not None else None
+        out = torch.empty(1, dtype=torch.float64, device=af.device)
+        _cabi.check(lib.impala_reduce(C.c_void_p(af.data_ptr()),
+                                      C.c_void_p(bf.data_ptr()) if bf is not None else None,
+                                      af.numel(), mode, C.c_void_p(out.data_ptr()), st), "impala_reduce")
+        ctx.mode, ctx.shape, ctx.dtype = mode, a.shape, a.dtype
+        ctx.save_for_backward(af, bf if bf is not None else af)
+        return out[0].to(a.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        af, bf = ctx.saved_tensors
+        if ctx.mode == 0:
+            ga = g.to(torch.float32).expand(af.shape)
+        elif ctx.mode == 1:
+            ga = g.to(torch.float32) * af
+        else:
+            ga = g.to(torch.float32) * bf
+        return ga.reshape(ctx.shape).to(ctx.dtype), None, None
+
+
+def action_log_probs(policy_logits, actions):
+    """log pi(a|x) of the taken actions, shaped like `actions` (learner.py:298-303)."""
+    return _PolicyTerms.apply(policy_logits, actions)[0].view_as(actions)
+
+
+def compute_baseline_loss(advantages):
+    """0.5 * sum(advantages ** 2)  (learner.py:306-307)."""
+    return _Reduce.apply(advantages, None, 1)
+
+
+def compute_entropy_loss(logits):
+    """The NEGATIVE entropy sum(p * log p), as in the reference (learner.py:310-314)."""
+    return _Reduce.apply(_PolicyTerms.apply(logits, torch.zeros(logits.shape[:-1], dtype=torch.int32,
+                                                                 device=logits.device))[1], None, 0)
+
+
+def compute_policy_gradient_loss(logits, actions, advantages):
+    """sum(-log pi(a|x) * advantages.detach())  (learner.py:317-321)."""
+    lp = _PolicyTerms.apply(logits, actions)[0]
+    return _Reduce.apply(lp, -advantages.detach().reshape(-1), 2)
