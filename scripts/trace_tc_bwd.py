@@ -21,7 +21,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 lib = _cabi.lib()
 lib._FuncPtr  # noqa: B018
-fn = lib.impala_debug_read_trace
+fn = lib.impala_debug_read_trace_unused
 fn.restype = C.c_int
 buf = (C.c_longlong * (3 * 4096))()
 n = fn(buf, 4096)

@@ -1,58 +1,47 @@
 // MLP backward on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated 3xTF32.
 //
 // Gradient of sum_m <dout[m,:], mlp(x[m,:])> w.r.t. (W1, b1, W2, b2)  (autograd at learner.py:175).
-// Transposed formulation so that a thread owns a HIDDEN unit (TMEM lane = hidden unit):
+// Transposed formulation so that a thread owns a HIDDEN unit (TMEM lane = hidden unit), per tile
+// of 64 batch rows:
 //
-//   UMMA1 (recompute)  PRE[H, 32]  = W1'[H, K'] * X'[32, K']^T     X' = [x | 1 | 0], W1' = [W1 | b1 | 0]
-//   CUDA cores         h = relu(PRE);  dh = W2^T dz;  dW2 += dz h;  DP = (PRE > 0) ? dh : 0
-//   UMMA2 (reduction)  dW1'[H, K'] += DP[H, 32] * X'[32, K']        column O of dW1' is db1
+//   UMMA1 (SS, recompute)  PRE[H, 64]  = W1'[H, K'] * X'[64, K']^T   X' = [x | 1 | 0], W1' = [W1 | b1 | 0]
+//   CUDA cores             h = relu(PRE);  dh = W2^T dz;  dW2 += dz h;  DP = (PRE > 0) ? dh : 0
+//   UMMA2 (TS, reduction)  dW1'[H, K'] += DP[H, 64] * X'[64, K']      column O of dW1' is db1
 //
-// per tile of 32 batch rows.  K' = 32 floats = one 128-byte swizzle row, so the W1', DP, X' and
-// X'^T tiles all share one shared-memory format (K-major rows of 128 B, SWIZZLE_128B).  The
-// producer writes every x tile twice: row-major (B of UMMA1, K = features) and transposed
-// (B of UMMA2, K = batch rows) - tf32 MN-major operands would need the 32-byte-swizzle
-// format, a second layout for the same bytes, so the transpose is done once on the way into
-// shared memory instead.  dW1' stays in TMEM for the whole
-// kernel (accumulated over every tile of the persistent CTA) and is read out once.  All
-// operands are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per
-// K step, which keeps the result within ~1e-6 relative of fp32.
+// PRE lands in TMEM; the epilogue thread that owns lane j reads its 64 pre-activations, and
+// writes DP back INTO TENSOR MEMORY (hi in place of PRE, lo in a second region) with tcgen05.st,
+// so UMMA2 takes its A operand from TMEM and only the small X'^T tile is fetched from shared
+// memory (with both operands in smem an M128xN32xK8 UMMA is operand-fetch bound at ~5x its math
+// time - measured).  dW1' accumulates in TMEM across every tile of the
+// persistent CTA and is read out once.  K' = 32 floats = one 128-byte swizzle row, so W1', X'
+// and X'^T tiles share one smem format (K-major, SWIZZLE_128B); the producer writes each x tile
+// row-major (B of UMMA1, K = features) and transposed (B of UMMA2, K = batch rows).  Operands
+// are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per K step.
 //
-// Warp roles (320 threads, one persistent CTA per SM):
-//   warps 0-7  epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
-//   warp  8    producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo swizzled tiles
-//   warp  9    TMEM allocator + single-thread UMMA issuer
+// TMEM map (512 columns): [0,256) two PRE/DP_hi buffers x (2 hidden blocks x 64 rows),
+//                         [256,384) DP_lo, [384,448) dW1' accumulators (2 blocks x 32 columns).
+// Warp roles (352 threads, one persistent CTA per SM):
+//   warps 0-7   epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
+//   warps 8-9   producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo tiles
+//   warp  10    TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
 #include <cstdlib>
 
 #include "mlp_kernels.cuh"
 #include "tc_common.cuh"
 
-// Debug timeline (IMPALA_TC_TRACE=1): CTA 0 records (event, tile, clock64) triples; read back
-// through impala_debug_read_trace (not part of the public ABI).
-__device__ long long g_trace[3 * 4096];
-__device__ int g_trace_n;
-
 namespace {
 
-__device__ __forceinline__ void trace(bool on, int ev, int tile) {
-    if (on) {
-        const int k = atomicAdd(&g_trace_n, 1);
-        if (k < 4096) {
-            g_trace[3 * k] = ev, g_trace[3 * k + 1] = tile, g_trace[3 * k + 2] = clock64();
-        }
-    }
-}
-
-constexpr int kRowsT = 32;       // batch rows per tile: N of UMMA1, K of UMMA2
+constexpr int kRowsT = 64;       // batch rows per tile: N of UMMA1, K of UMMA2
 constexpr int kKPad = 32;        // padded feature count K' (data + bias column + zeros)
 constexpr int kXStages = 3;      // converted x / x^T / dz stages
 constexpr int kRawStages = 4;    // bulk-copy ring depth
-constexpr int kD1Stages = 4;     // TMEM stages of PRE
-constexpr int kThreads = 10 * 32;
-constexpr int kWTileBytes = 256 * 128;     // 256 hidden rows x 128 B
-constexpr int kXTileBytes = kRowsT * 128;  // 4 KiB
-constexpr int kRawStageBytes = 4096;       // x rows (<= 32*28*4 = 3584 B) | dout rows at +3584
-constexpr int kRawDzOffset = 3584;
-constexpr int kAccCol = 256;               // TMEM column of the dW1' accumulators
+constexpr int kThreads = 11 * 32;
+constexpr int kWTileBytes = 256 * 128;      // 256 hidden rows x 128 B
+constexpr int kXTileBytes = kRowsT * 128;   // 8 KiB: 64 rows x 128 B (also 2 x [32 rows x 128 B])
+constexpr int kRawStageBytes = 8192;        // x rows (<= 64*28*4 = 7168 B) | dout rows at +7168
+constexpr int kRawDzOffset = 7168;
+constexpr int kColLo = 256;                 // TMEM column of DP_lo
+constexpr int kColAcc = 384;                // TMEM column of the dW1' accumulators
 
 struct BwdTcArgs {
     const float* x;
@@ -60,13 +49,12 @@ struct BwdTcArgs {
     const float* dout;
     float* ws;
     int M, O, H, N2, num_tiles;
-    int trace;
     MlpLayout lay;
 };
 
 struct __align__(8) Barriers {
     uint64_t raw_full[kRawStages], full[kXStages], empty[kXStages];
-    uint64_t d1_full[kD1Stages], d1_empty[kD1Stages], dp_full, dp_free, done;
+    uint64_t d1_full[2], dp_full[2], lo_free, done;
     uint32_t tmem_base;
 };
 
@@ -77,14 +65,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                                                ~static_cast<uintptr_t>(1023));
     uint8_t* w_hi = smem;
     uint8_t* w_lo = w_hi + kWTileBytes;
-    uint8_t* dp_hi = w_lo + kWTileBytes;
-    uint8_t* dp_lo = dp_hi + kWTileBytes;
-    uint8_t* x_hi = dp_lo + kWTileBytes;              // kXStages tiles
+    uint8_t* x_hi = w_lo + kWTileBytes;               // kXStages tiles, [64 rows][128 B]
     uint8_t* x_lo = x_hi + kXStages * kXTileBytes;
-    uint8_t* xt_hi = x_lo + kXStages * kXTileBytes;   // transposed tiles: row = feature, col = batch row
+    uint8_t* xt_hi = x_lo + kXStages * kXTileBytes;   // transposed: 2 K-chunks x [32 features][128 B]
     uint8_t* xt_lo = xt_hi + kXStages * kXTileBytes;
-    uint8_t* raw = xt_lo + kXStages * kXTileBytes;    // kRawStages x 4 KiB
-    float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][32][NP]
+    uint8_t* raw = xt_lo + kXStages * kXTileBytes;    // kRawStages x 8 KiB
+    float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][64][NP]
     Barriers* bars = reinterpret_cast<Barriers*>(dzs + kXStages * kRowsT * NP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,8 +79,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     const float* __restrict__ W2 = a.params + a.lay.oW2;
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
     const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp >= 8);
-    trace(tr && warp == 0, 0, -1);
 
     // ---- one-time setup
     for (int idx = tid; idx < H * 8; idx += kThreads) {
@@ -112,20 +96,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         *reinterpret_cast<float4*>(w_lo + off) = lo;
     }
     tc::fence_proxy_async();
-    if (warp == 9) {
+    if (warp == 10) {
         tc::tmem_alloc(&bars->tmem_base, 512);
         if (lane == 0) {
             for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
             for (int s = 0; s < kXStages; ++s) {
-                tc::mbar_init(&bars->full[s], 32);
-                tc::mbar_init(&bars->empty[s], 1);
+                tc::mbar_init(&bars->full[s], 64);   // every producer thread arrives
+                tc::mbar_init(&bars->empty[s], 1);   // tcgen05.commit after UMMA2
             }
-            for (int s = 0; s < kD1Stages; ++s) {
-                tc::mbar_init(&bars->d1_full[s], 1);
-                tc::mbar_init(&bars->d1_empty[s], nblk * 128);
+            for (int s = 0; s < 2; ++s) {
+                tc::mbar_init(&bars->d1_full[s], 1);           // tcgen05.commit after UMMA1
+                tc::mbar_init(&bars->dp_full[s], nblk * 128);  // every active epilogue thread
             }
-            tc::mbar_init(&bars->dp_full, nblk * 128);
-            tc::mbar_init(&bars->dp_free, 1);
+            tc::mbar_init(&bars->lo_free, 1);  // tcgen05.commit after UMMA2
             tc::mbar_init(&bars->done, 1);
             tc::mbar_fence_init();
         }
@@ -149,62 +132,55 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % kXStages, ph = (i / kXStages) & 1;
-                const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
-                trace(tr, 10, i);
-                tc::mbar_wait(&bars->full[s], ph);      // dz rows of this tile are visible
+                const int d1 = i & 1, dph = (i >> 1) & 1;
+                const uint32_t c_hi = lane_addr + d1 * 128 + blk * 64;   // PRE in, DP_hi out
+                const uint32_t c_lo = lane_addr + kColLo + blk * 64;
+                tc::mbar_wait(&bars->full[s], ph);       // dz rows of this tile are visible
                 tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
-                trace(tr, 11, i);
-                float v[32];
-                tc::tmem_ld32(lane_addr + d1 * 64 + blk * 32, v);
-                tc::tc_fence_before();
-                tc::mbar_arrive(&bars->d1_empty[d1]);
                 const float* dz_tile = dzs + s * kRowsT * NP;
-#pragma unroll
-                for (int r = 0; r < kRowsT; ++r) {
-                    float dz[NP];
-                    if constexpr (NP == 4) {
-                        const float4 t = *reinterpret_cast<const float4*>(dz_tile + r * 4);
-                        dz[0] = t.x, dz[1] = t.y, dz[2] = t.z, dz[3] = t.w;
-                    } else {
-                        dz[0] = dz_tile[r];
-                    }
-                    const float pre = v[r], h = fmaxf(pre, 0.f);
-                    float dh = 0.f;
-#pragma unroll
-                    for (int n = 0; n < NP; ++n) {
-                        dh = fmaf(dz[n], w2r[n], dh);
-                        gw2[n] = fmaf(dz[n], h, gw2[n]);
-                    }
-                    v[r] = pre > 0.f ? dh : 0.f;  // relu'(0) = 0 as in torch
-                }
                 if (tid < a.N2) {
                     for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[r * NP + tid];
                 }
-                trace(tr, 12, i);
-                tc::mbar_wait(&bars->dp_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
-                trace(tr, 13, i);
+                float lo[2][32];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 hi, lo;
-                    tc::split_tf32(v[4 * c + 0], hi.x, lo.x);
-                    tc::split_tf32(v[4 * c + 1], hi.y, lo.y);
-                    tc::split_tf32(v[4 * c + 2], hi.z, lo.z);
-                    tc::split_tf32(v[4 * c + 3], hi.w, lo.w);
-                    const uint32_t off = blk * (128 * 128) + tc::sw128_offset(jl, c);
-                    *reinterpret_cast<float4*>(dp_hi + off) = hi;
-                    *reinterpret_cast<float4*>(dp_lo + off) = lo;
+                for (int hh = 0; hh < 2; ++hh) {  // two halves of 32 batch rows
+                    float v[32];
+                    tc::tmem_ld32(c_hi + 32 * hh, v);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        float dz[NP];
+                        if constexpr (NP == 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(dz_tile + (32 * hh + r) * 4);
+                            dz[0] = t.x, dz[1] = t.y, dz[2] = t.z, dz[3] = t.w;
+                        } else {
+                            dz[0] = dz_tile[32 * hh + r];
+                        }
+                        const float pre = v[r], h = fmaxf(pre, 0.f);
+                        float dh = 0.f;
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) {
+                            dh = fmaf(dz[n], w2r[n], dh);
+                            gw2[n] = fmaf(dz[n], h, gw2[n]);
+                        }
+                        const float dp = pre > 0.f ? dh : 0.f;  // relu'(0) = 0 as in torch
+                        tc::split_tf32(dp, v[r], lo[hh][r]);
+                    }
+                    tc::tmem_st32(c_hi + 32 * hh, v);  // DP_hi replaces PRE in place
                 }
-                tc::fence_proxy_async();
-                tc::mbar_arrive(&bars->dp_full);
-                trace(tr, 14, i);
+                tc::mbar_wait(&bars->lo_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
+                tc::tc_fence_after();
+                tc::tmem_st32(c_lo, lo[0]);
+                tc::tmem_st32(c_lo + 32, lo[1]);
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars->dp_full[d1]);
             }
             // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
             tc::mbar_wait(&bars->done, 0);
             tc::tc_fence_after();
-            trace(tr, 15, n_my);
             float g[32];
-            tc::tmem_ld32(lane_addr + kAccCol + blk * 32, g);
+            tc::tmem_ld32(lane_addr + kColAcc + blk * 32, g);
             float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
@@ -225,13 +201,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int sgm = 0; sgm < 4; ++sgm)
                 for (int64_t p = lo4[sgm] + tid; p < hi4[sgm]; p += 256) wsb[p] = 0.f;
         }
-    } else if (warp == 8) {
-        // =============================== producer ===============================
+    } else if (warp < 10) {
+        // ===================== producer (2 warps, 32 rows of the tile each) =====================
+        const int pw = warp - 8, r = 32 * pw + lane;  // row of the tile this thread converts
         const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
         auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kRowsT <= a.M; };
         auto issue_raw = [&](int i) {
-            if (lane == 0 && is_full(i)) {
+            if (pw == 0 && lane == 0 && is_full(i)) {
                 const int rs = i % kRawStages;
                 uint8_t* dst = raw + rs * kRawStageBytes;
                 const size_t row0 = (size_t)tile_of(i) * kRowsT;
@@ -251,12 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NP; ++n) z[n] = 0.f;
-            trace(tr, 20, i);
             if (is_full(i)) {
                 tc::mbar_wait(&bars->raw_full[rs], rph);
-                trace(tr, 21, i);
-                const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + lane * ochunks;
-                const float* rz = reinterpret_cast<const float*>(raw + rs * kRawStageBytes + kRawDzOffset) + lane * a.N2;
+                const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + r * ochunks;
+                const float* rz = reinterpret_cast<const float*>(raw + rs * kRawStageBytes + kRawDzOffset) + r * a.N2;
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c < ochunks) v[c] = rx[c];
@@ -264,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 for (int n = 0; n < NP; ++n)
                     if (n < a.N2) z[n] = rz[n];
             } else {  // ragged last tile: plain guarded loads
-                const int row = tile_of(i) * kRowsT + lane;
+                const int row = tile_of(i) * kRowsT + r;
                 if (row < a.M) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -277,13 +252,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1 / collects db1
-            __syncwarp();
-            if (i + kRawStages < n_my) issue_raw(i + kRawStages);  // refill the stage just drained
-            trace(tr, 22, i);
+            asm volatile("bar.sync 1, 64;" ::: "memory");  // both producer warps drained the raw stage
+            if (i + kRawStages < n_my) issue_raw(i + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
-            trace(tr, 23, i);
             uint8_t* th = x_hi + s * kXTileBytes;
             uint8_t* tl = x_lo + s * kXTileBytes;
+            // transposed tiles: K-chunk pw (32 batch rows), row = feature, column = lane
+            uint8_t* tth = xt_hi + s * kXTileBytes + pw * 4096 + (lane & 3) * 4;
+            uint8_t* ttl = xt_lo + s * kXTileBytes + pw * 4096 + (lane & 3) * 4;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 hi, lo;
@@ -291,12 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 tc::split_tf32(v[c].y, hi.y, lo.y);
                 tc::split_tf32(v[c].z, hi.z, lo.z);
                 tc::split_tf32(v[c].w, hi.w, lo.w);
-                const uint32_t off = tc::sw128_offset(lane, c);
+                const uint32_t off = tc::sw128_offset(r, c);
                 *reinterpret_cast<float4*>(th + off) = hi;
                 *reinterpret_cast<float4*>(tl + off) = lo;
-                // transposed copy: element (feature 4c+e, batch row `lane`)
-                uint8_t* tth = xt_hi + s * kXTileBytes + (lane & 3) * 4;
-                uint8_t* ttl = xt_lo + s * kXTileBytes + (lane & 3) * 4;
                 const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -306,74 +279,68 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 }
             }
 #pragma unroll
-            for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + lane) * NP + n] = z[n];
+            for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + r) * NP + n] = z[n];
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
-            trace(tr, 24, i);
         }
     } else {
         // =============================== UMMA issuer ===============================
         // The whole warp runs the schedule (warp-uniform descriptors stay in uniform registers);
-        // one elected lane issues the UMMAs and their commits.
-        const uint32_t idesc = tc::instr_desc_tf32_m128(kRowsT);  // N = 32 for both UMMAs
+        // one elected lane issues the UMMAs and their commits.  UMMAs execute in issue order, so
+        // UMMA1(i+2) overwriting the PRE/DP_hi buffer that UMMA2(i) reads needs no extra barrier.
+        const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 64 batch rows
+        const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);   // N = 32 feature columns
         const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
         const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
-        const uint64_t dp_hi_d = tc::smem_desc_k_sw128(dp_hi, 0), dp_lo_d = tc::smem_desc_k_sw128(dp_lo, 0);
         const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
         const uint64_t dxt_hi = tc::smem_desc_k_sw128(xt_hi, 0), dxt_lo = tc::smem_desc_k_sw128(xt_lo, 0);
-        constexpr uint64_t kBlkOff = (128 * 128) >> 4;  // next 128-row block of a 256-row tile
+        constexpr uint64_t kBlkOff = (128 * 128) >> 4;  // next 128-row block of the W1' tile
         auto issue_umma1 = [&](int i) {
-            const int s = i % kXStages, ph = (i / kXStages) & 1;
-            const int d1 = i % kD1Stages, dph = (i / kD1Stages) & 1;
-            trace(tr, 30, i);
+            const int s = i % kXStages, ph = (i / kXStages) & 1, d1 = i & 1;
             tc::mbar_wait(&bars->full[s], ph);
-            tc::mbar_wait(&bars->d1_empty[d1], dph ^ 1);
             tc::tc_fence_after();
-            trace(tr, 31, i);
             if (tc::elect_one()) {
                 const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
 #pragma unroll 1
                 for (int b = 0; b < nblk; ++b) {
-                    const uint32_t d = tmem_base + d1 * 64 + b * 32;
+                    const uint32_t d = tmem_base + d1 * 128 + b * 64;
 #pragma unroll 1
                     for (int kk = 0; kk < ksteps1; ++kk) {
                         const uint64_t ko = 2 * kk, bo = b * kBlkOff;
-                        tc::umma_tf32(d, dw_hi + bo + ko, dx_hi + so + ko, idesc, kk > 0);
-                        tc::umma_tf32(d, dw_lo + bo + ko, dx_hi + so + ko, idesc, true);
-                        tc::umma_tf32(d, dw_hi + bo + ko, dx_lo + so + ko, idesc, true);
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_hi + so + ko, idesc1, kk > 0);
+                        tc::umma_tf32(d, dw_lo + bo + ko, dx_hi + so + ko, idesc1, true);
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_lo + so + ko, idesc1, true);
                     }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
             }
             __syncwarp();
-            trace(tr, 32, i);
         };
         if (n_my > 0) issue_umma1(0);
         if (n_my > 1) issue_umma1(1);
         for (int i = 0; i < n_my; ++i) {
-            const int s = i % kXStages;
-            trace(tr, 33, i);
-            tc::mbar_wait(&bars->dp_full, i & 1);  // DP tiles of tile i are in shared memory
+            const int s = i % kXStages, d1 = i & 1;
+            tc::mbar_wait(&bars->dp_full[d1], (i >> 1) & 1);  // DP hi/lo of tile i are in TMEM
             tc::tc_fence_after();
-            trace(tr, 34, i);
             if (tc::elect_one()) {
                 const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
 #pragma unroll 1
                 for (int b = 0; b < nblk; ++b) {
-                    const uint32_t d = tmem_base + kAccCol + b * 32;
+                    const uint32_t d = tmem_base + kColAcc + b * 32;
+                    const uint32_t a_hi = tmem_base + d1 * 128 + b * 64, a_lo = tmem_base + kColLo + b * 64;
 #pragma unroll 1
-                    for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 32 batch rows, 8 per step
-                        const uint64_t ko = 2 * kk, bo = b * kBlkOff;
-                        tc::umma_tf32(d, dp_hi_d + bo + ko, dxt_hi + so + ko, idesc, i > 0 || kk > 0);
-                        tc::umma_tf32(d, dp_lo_d + bo + ko, dxt_hi + so + ko, idesc, true);
-                        tc::umma_tf32(d, dp_hi_d + bo + ko, dxt_lo + so + ko, idesc, true);
+                    for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
+                        // x^T tile: K-chunk kk/4 (4 KiB each), 32 bytes per step inside the chunk
+                        const uint64_t ko = static_cast<uint64_t>(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt_hi + so + ko, idesc2, i > 0 || kk > 0);
+                        tc::umma_tf32_ts(d, a_lo + 8 * kk, dxt_hi + so + ko, idesc2, true);
+                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt_lo + so + ko, idesc2, true);
                     }
                 }
-                tc::umma_commit(&bars->dp_free);   // DP tiles reusable
-                tc::umma_commit(&bars->empty[s]);  // x / dz stage reusable
+                tc::umma_commit(&bars->lo_free);   // DP_lo region reusable
+                tc::umma_commit(&bars->empty[s]);  // x / x^T / dz stage reusable
             }
             __syncwarp();
-            trace(tr, 35, i);
             if (i + 2 < n_my) issue_umma1(i + 2);
         }
         if (tc::elect_one()) tc::umma_commit(&bars->done);
@@ -382,13 +349,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 10) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
-constexpr size_t kSmemBytes = 1024 + 4 * kWTileBytes + 4 * kXStages * kXTileBytes +
+constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +
                               kRawStages * kRawStageBytes + kXStages * kRowsT * 4 * sizeof(float) +
                               sizeof(Barriers);
 
@@ -409,12 +376,6 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
     a.num_tiles = (M + kRowsT - 1) / kRowsT;
     a.lay = impala_make_layout(O, H, N2);
-    const char* tr_env = std::getenv("IMPALA_TC_TRACE");
-    a.trace = tr_env && tr_env[0] == '1';
-    if (a.trace) {
-        const int zero = 0;
-        cudaMemcpyToSymbolAsync(g_trace_n, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, st);
-    }
     static int sms = 0;
     static bool opted[2] = {false, false};
     cudaError_t e;
@@ -436,15 +397,4 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     *grid_out = grid;
     return impala_launch_status();
-}
-
-// Debug only: copies up to n (event, tile, clock) triples of the last traced launch; returns count.
-extern "C" int impala_debug_read_trace(long long* out, int n) {
-    int cnt = 0;
-    cudaDeviceSynchronize();
-    if (cudaMemcpyFromSymbol(&cnt, g_trace_n, sizeof(int)) != cudaSuccess) return -1;
-    if (cnt > 4096) cnt = 4096;
-    if (cnt > n) cnt = n;
-    if (cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * cnt) != cudaSuccess) return -1;
-    return cnt;
 }
