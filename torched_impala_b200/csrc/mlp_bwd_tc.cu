@@ -29,6 +29,11 @@
 #include "mlp_kernels.cuh"
 #include "tc_common.cuh"
 
+// Debug timeline (IMPALA_TC_TRACE=1): CTA 0 keeps clock64() stamps of its pipeline events in
+// shared memory and dumps them at exit; read back through impala_debug_read_trace (not part of
+// the public ABI).  Layout: [tile < 24][event < 16].
+__device__ long long g_trace[24 * 16];
+
 namespace {
 
 constexpr int kRowsT = 64;       // batch rows per tile: N of UMMA1, K of UMMA2
@@ -49,6 +54,7 @@ struct BwdTcArgs {
     const float* dout;
     float* ws;
     int M, O, H, N2, num_tiles;
+    int trace;
     MlpLayout lay;
 };
 
@@ -79,6 +85,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     const float* __restrict__ W2 = a.params + a.lay.oW2;
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
     const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    __shared__ long long s_trace[24 * 16];
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 10);
+#define TRACE(tile, ev)                                              \
+    if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
+    if (a.trace && blockIdx.x == 0)
+        for (int k = tid; k < 24 * 16; k += kThreads) s_trace[k] = 0;
+    TRACE(0, 15)
 
     // ---- one-time setup
     for (int idx = tid; idx < H * 8; idx += kThreads) {
@@ -135,9 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 const int d1 = i & 1, dph = (i >> 1) & 1;
                 const uint32_t c_hi = lane_addr + d1 * 128 + blk * 64;   // PRE in, DP_hi out
                 const uint32_t c_lo = lane_addr + kColLo + blk * 64;
+                TRACE(i, 0)
                 tc::mbar_wait(&bars->full[s], ph);       // dz rows of this tile are visible
                 tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
+                TRACE(i, 1)
                 const float* dz_tile = dzs + s * kRowsT * NP;
                 if (tid < a.N2) {
                     for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[r * NP + tid];
@@ -168,13 +183,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                     }
                     tc::tmem_st32(c_hi + 32 * hh, v);  // DP_hi replaces PRE in place
                 }
+                TRACE(i, 2)
                 tc::mbar_wait(&bars->lo_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
                 tc::tc_fence_after();
+                TRACE(i, 3)
                 tc::tmem_st32(c_lo, lo[0]);
                 tc::tmem_st32(c_lo + 32, lo[1]);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars->dp_full[d1]);
+                TRACE(i, 4)
             }
             // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
             tc::mbar_wait(&bars->done, 0);
@@ -228,8 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NP; ++n) z[n] = 0.f;
+            TRACE(i, 5)
             if (is_full(i)) {
                 tc::mbar_wait(&bars->raw_full[rs], rph);
+                TRACE(i, 6)
                 const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + r * ochunks;
                 const float* rz = reinterpret_cast<const float*>(raw + rs * kRawStageBytes + kRawDzOffset) + r * a.N2;
 #pragma unroll
@@ -255,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             asm volatile("bar.sync 1, 64;" ::: "memory");  // both producer warps drained the raw stage
             if (i + kRawStages < n_my) issue_raw(i + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
+            TRACE(i, 7)
             uint8_t* th = x_hi + s * kXTileBytes;
             uint8_t* tl = x_lo + s * kXTileBytes;
             // transposed tiles: K-chunk pw (32 batch rows), row = feature, column = lane
@@ -282,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + r) * NP + n] = z[n];
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
+            TRACE(i, 8)
         }
     } else {
         // =============================== UMMA issuer ===============================
@@ -297,8 +319,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         constexpr uint64_t kBlkOff = (128 * 128) >> 4;  // next 128-row block of the W1' tile
         auto issue_umma1 = [&](int i) {
             const int s = i % kXStages, ph = (i / kXStages) & 1, d1 = i & 1;
+            TRACE(i, 9)
             tc::mbar_wait(&bars->full[s], ph);
             tc::tc_fence_after();
+            TRACE(i, 10)
             if (tc::elect_one()) {
                 const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
 #pragma unroll 1
@@ -315,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 tc::umma_commit(&bars->d1_full[d1]);
             }
             __syncwarp();
+            TRACE(i, 11)
         };
         if (n_my > 0) issue_umma1(0);
         if (n_my > 1) issue_umma1(1);
@@ -322,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             const int s = i % kXStages, d1 = i & 1;
             tc::mbar_wait(&bars->dp_full[d1], (i >> 1) & 1);  // DP hi/lo of tile i are in TMEM
             tc::tc_fence_after();
+            TRACE(i, 12)
             if (tc::elect_one()) {
                 const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
 #pragma unroll 1
@@ -341,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                 tc::umma_commit(&bars->empty[s]);  // x / x^T / dz stage reusable
             }
             __syncwarp();
+            TRACE(i, 13)
             if (i + 2 < n_my) issue_umma1(i + 2);
         }
         if (tc::elect_one()) tc::umma_commit(&bars->done);
@@ -353,6 +380,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    if (a.trace && blockIdx.x == 0) {
+        if (tid == 0) s_trace[1 * 16 + 15] = clock64();
+        __syncthreads();
+        for (int k = tid; k < 24 * 16; k += kThreads) g_trace[k] = s_trace[k];
+    }
+#undef TRACE
 }
 
 constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +
@@ -376,6 +409,8 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
     a.num_tiles = (M + kRowsT - 1) / kRowsT;
     a.lay = impala_make_layout(O, H, N2);
+    const char* tr_env = std::getenv("IMPALA_TC_TRACE");
+    a.trace = tr_env && tr_env[0] == '1';
     static int sms = 0;
     static bool opted[2] = {false, false};
     cudaError_t e;
@@ -397,4 +432,12 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     *grid_out = grid;
     return impala_launch_status();
+}
+
+// Debug only: the [24 tiles][16 events] clock stamps of the last traced launch (CTA 0).
+extern "C" int impala_debug_read_trace(long long* out, int n) {
+    cudaDeviceSynchronize();
+    if (n > 24 * 16) n = 24 * 16;
+    if (cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * n) != cudaSuccess) return -1;
+    return n;
 }
