@@ -1,4 +1,4 @@
-"""Timeline of CTA 0 of the tcgen05 backward (IMPALA_TC_TRACE=1)."""
+"""Pipeline timeline of CTA 0 of the tcgen05 backward (IMPALA_TC_TRACE=1); cycles since kernel start."""
 import ctypes as C
 import os
 import sys
@@ -19,20 +19,16 @@ pp = ops.pack_params(p)
 for _ in range(3):
     ops.mlp_backward(x, pp, d, O, H, N2)
 torch.cuda.synchronize()
-lib = _cabi.lib()
-lib._FuncPtr  # noqa: B018
-fn = lib.impala_debug_read_trace_unused
+fn = _cabi.lib().impala_debug_read_trace
 fn.restype = C.c_int
-buf = (C.c_longlong * (3 * 4096))()
-n = fn(buf, 4096)
-ev = np.array(buf[: 3 * n], dtype=np.int64).reshape(n, 3)
-t0 = ev[:, 2].min()
-names = {0: "start", 10: "E.begin", 11: "E.d1_full", 12: "E.math_done", 13: "E.dp_free", 14: "E.dp_full",
-         15: "E.done", 20: "P.begin", 21: "P.raw_ok", 22: "P.loaded", 23: "P.empty_ok", 24: "P.full",
-         30: "M1.begin", 31: "M1.ready", 32: "M1.issued", 33: "M2.wait", 34: "M2.ready", 35: "M2.issued"}
-order = np.argsort(ev[:, 2], kind="stable")
-print(f"{n} events")
-for k in order:
-    e, tile, t = ev[k]
-    if tile <= 5 or tile >= 17:
-        print(f"{t - t0:8d}  tile {tile:3d}  {names.get(int(e), e)}")
+buf = (C.c_longlong * (24 * 16))()
+fn(buf, 24 * 16)
+t = np.array(buf[:], dtype=np.int64).reshape(24, 16)
+t0 = t[0, 15]
+names = ["E.begin", "E.d1_full", "E.math_done", "E.lo_free", "E.dp_full", "P.begin", "P.raw_ok", "P.empty_ok",
+         "P.full", "M1.begin", "M1.ready", "M1.issued", "M2.ready", "M2.issued"]
+print("kernel cycles (CTA 0):", t[1, 15] - t0)
+print("tile " + " ".join(f"{n:>11s}" for n in names))
+for i in range(24):
+    if t[i, :14].any():
+        print(f"{i:4d} " + " ".join(f"{(v - t0) if v else 0:11d}" for v in t[i, :14]))
