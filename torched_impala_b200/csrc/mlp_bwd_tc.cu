@@ -18,8 +18,13 @@
 // row-major (B of UMMA1, K = features) and transposed (B of UMMA2, K = batch rows).  Operands
 // are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per K step.
 //
+// UMMA2 issues two instead of three products per K step: the x^T tile stacks the hi and lo
+// features as 64 rows, so  DP_hi x [X'^T_hi ; X'^T_lo]  (N = 64) yields dp_hi*x_hi and dp_hi*x_lo
+// in adjacent accumulator columns (summed at read-out) and  DP_lo x X'^T_hi  (N = 32) adds the
+// third term - small-N UMMAs cost ~40 cycles each regardless of N, so fewer, wider ones win.
+//
 // TMEM map (512 columns): [0,256) two PRE/DP_hi buffers x (2 hidden blocks x 64 rows),
-//                         [256,384) DP_lo, [384,448) dW1' accumulators (2 blocks x 32 columns).
+//                         [256,384) DP_lo, [384,512) dW1' accumulators (2 blocks x (32 + 32)).
 // Warp roles (352 threads, one persistent CTA per SM):
 //   warps 0-7   epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
 //   warps 8-9   producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo tiles
@@ -73,9 +78,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     uint8_t* w_lo = w_hi + kWTileBytes;
     uint8_t* x_hi = w_lo + kWTileBytes;               // kXStages tiles, [64 rows][128 B]
     uint8_t* x_lo = x_hi + kXStages * kXTileBytes;
-    uint8_t* xt_hi = x_lo + kXStages * kXTileBytes;   // transposed: 2 K-chunks x [32 features][128 B]
-    uint8_t* xt_lo = xt_hi + kXStages * kXTileBytes;
-    uint8_t* raw = xt_lo + kXStages * kXTileBytes;    // kRawStages x 8 KiB
+    // transposed tiles: per stage 2 K-chunks (32 batch rows each) x [64 rows][128 B], rows 0-31 =
+    // hi of feature n, rows 32-63 = lo of feature n
+    uint8_t* xt = x_lo + kXStages * kXTileBytes;
+    uint8_t* raw = xt + 2 * kXStages * kXTileBytes;   // kRawStages x 8 KiB
     float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][64][NP]
     Barriers* bars = reinterpret_cast<Barriers*>(dzs + kXStages * kRowsT * NP);
 
@@ -197,8 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
             tc::mbar_wait(&bars->done, 0);
             tc::tc_fence_after();
-            float g[32];
-            tc::tmem_ld32(lane_addr + kColAcc + blk * 32, g);
+            float g[32], g2[32];
+            tc::tmem_ld32(lane_addr + kColAcc + blk * 64, g);        // dp_hi*x_hi + dp_lo*x_hi
+            tc::tmem_ld32(lane_addr + kColAcc + blk * 64 + 32, g2);  // dp_hi*x_lo
+#pragma unroll
+            for (int k = 0; k < 32; ++k) g[k] += g2[k];
             float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
@@ -278,9 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             TRACE(i, 7)
             uint8_t* th = x_hi + s * kXTileBytes;
             uint8_t* tl = x_lo + s * kXTileBytes;
-            // transposed tiles: K-chunk pw (32 batch rows), row = feature, column = lane
-            uint8_t* tth = xt_hi + s * kXTileBytes + pw * 4096 + (lane & 3) * 4;
-            uint8_t* ttl = xt_lo + s * kXTileBytes + pw * 4096 + (lane & 3) * 4;
+            // transposed tile of K-chunk pw (this warp's 32 batch rows): row = feature (+32 for lo)
+            uint8_t* tth = xt + (2 * s + pw) * kXTileBytes + (lane & 3) * 4;
+            uint8_t* ttl = tth + 32 * 128;  // rows 32..63 (32 is a multiple of the 8-row swizzle period)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 hi, lo;
@@ -311,11 +320,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         // one elected lane issues the UMMAs and their commits.  UMMAs execute in issue order, so
         // UMMA1(i+2) overwriting the PRE/DP_hi buffer that UMMA2(i) reads needs no extra barrier.
         const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 64 batch rows
-        const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);   // N = 32 feature columns
+        const uint32_t idesc2w = tc::instr_desc_tf32_m128(2 * kKPad);  // N = 64: [hi | lo] features
+        const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);       // N = 32: hi features
         const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
         const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
         const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
-        const uint64_t dxt_hi = tc::smem_desc_k_sw128(xt_hi, 0), dxt_lo = tc::smem_desc_k_sw128(xt_lo, 0);
+        const uint64_t dxt = tc::smem_desc_k_sw128(xt, 0);
         constexpr uint64_t kBlkOff = (128 * 128) >> 4;  // next 128-row block of the W1' tile
         auto issue_umma1 = [&](int i) {
             const int s = i % kXStages, ph = (i / kXStages) & 1, d1 = i & 1;
@@ -349,18 +359,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             tc::tc_fence_after();
             TRACE(i, 12)
             if (tc::elect_one()) {
-                const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
 #pragma unroll 1
                 for (int b = 0; b < nblk; ++b) {
-                    const uint32_t d = tmem_base + kColAcc + b * 32;
+                    const uint32_t d = tmem_base + kColAcc + b * 64;
                     const uint32_t a_hi = tmem_base + d1 * 128 + b * 64, a_lo = tmem_base + kColLo + b * 64;
 #pragma unroll 1
                     for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
-                        // x^T tile: K-chunk kk/4 (4 KiB each), 32 bytes per step inside the chunk
-                        const uint64_t ko = static_cast<uint64_t>(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
-                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt_hi + so + ko, idesc2, i > 0 || kk > 0);
-                        tc::umma_tf32_ts(d, a_lo + 8 * kk, dxt_hi + so + ko, idesc2, true);
-                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt_lo + so + ko, idesc2, true);
+                        // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
+                        const uint64_t ko = static_cast<uint64_t>(
+                            (((2 * s + (kk >> 2)) * kXTileBytes) + (kk & 3) * 32) >> 4);
+                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt + ko, idesc2w, i > 0 || kk > 0);
+                        tc::umma_tf32_ts(d, a_lo + 8 * kk, dxt + ko, idesc2, true);
                     }
                 }
                 tc::umma_commit(&bars->lo_free);   // DP_lo region reusable
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
 #undef TRACE
 }
 
-constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +
+constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +  // x hi/lo + x^T (2 chunks)
                               kRawStages * kRawStageBytes + kXStages * kRowsT * 4 * sizeof(float) +
                               sizeof(Barriers);
 
