@@ -335,22 +335,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             TRACE(i, 10)
             if (tc::elect_one()) {
                 const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
-                // blocks interleaved: consecutive UMMAs accumulate into different TMEM tiles
 #pragma unroll 1
-                for (int kk = 0; kk < ksteps1; ++kk) {
-                    const uint64_t ko = 2 * kk;
+                for (int b = 0; b < nblk; ++b) {
+                    const uint32_t d = tmem_base + d1 * 128 + b * 64;
 #pragma unroll 1
-                    for (int b = 0; b < nblk; ++b)
-                        tc::umma_tf32(tmem_base + d1 * 128 + b * 64, dw_hi + b * kBlkOff + ko,
-                                      dx_hi + so + ko, idesc1, kk > 0);
-#pragma unroll 1
-                    for (int b = 0; b < nblk; ++b)
-                        tc::umma_tf32(tmem_base + d1 * 128 + b * 64, dw_lo + b * kBlkOff + ko,
-                                      dx_hi + so + ko, idesc1, true);
-#pragma unroll 1
-                    for (int b = 0; b < nblk; ++b)
-                        tc::umma_tf32(tmem_base + d1 * 128 + b * 64, dw_hi + b * kBlkOff + ko,
-                                      dx_lo + so + ko, idesc1, true);
+                    for (int kk = 0; kk < ksteps1; ++kk) {
+                        const uint64_t ko = 2 * kk, bo = b * kBlkOff;
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_hi + so + ko, idesc1, kk > 0);
+                        tc::umma_tf32(d, dw_lo + bo + ko, dx_hi + so + ko, idesc1, true);
+                        tc::umma_tf32(d, dw_hi + bo + ko, dx_lo + so + ko, idesc1, true);
+                    }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
             }
@@ -365,21 +359,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             tc::tc_fence_after();
             TRACE(i, 12)
             if (tc::elect_one()) {
-                // A dependent chain of small UMMAs runs at the pipe's latency (~65 cycles each), not
-                // its throughput: interleave the two hidden blocks so neighbours are independent.
 #pragma unroll 1
-                for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
-                    // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
-                    const uint64_t ko = static_cast<uint64_t>(
-                        (((2 * s + (kk >> 2)) * kXTileBytes) + (kk & 3) * 32) >> 4);
+                for (int b = 0; b < nblk; ++b) {
+                    const uint32_t d = tmem_base + kColAcc + b * 64;
+                    const uint32_t a_hi = tmem_base + d1 * 128 + b * 64, a_lo = tmem_base + kColLo + b * 64;
 #pragma unroll 1
-                    for (int b = 0; b < nblk; ++b)
-                        tc::umma_tf32_ts(tmem_base + kColAcc + b * 64, tmem_base + d1 * 128 + b * 64 + 8 * kk,
-                                         dxt + ko, idesc2w, i > 0 || kk > 0);
-#pragma unroll 1
-                    for (int b = 0; b < nblk; ++b)
-                        tc::umma_tf32_ts(tmem_base + kColAcc + b * 64, tmem_base + kColLo + b * 64 + 8 * kk,
-                                         dxt + ko, idesc2, true);
+                    for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
+                        // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
+                        const uint64_t ko = static_cast<uint64_t>(
+                            (((2 * s + (kk >> 2)) * kXTileBytes) + (kk & 3) * 32) >> 4);
+                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt + ko, idesc2w, i > 0 || kk > 0);
+                        tc::umma_tf32_ts(d, a_lo + 8 * kk, dxt + ko, idesc2, true);
+                    }
                 }
                 tc::umma_commit(&bars->lo_free);   // DP_lo region reusable
                 tc::umma_commit(&bars->empty[s]);  // x / x^T / dz stage reusable
