@@ -13,12 +13,18 @@
 //
 // Warp roles (288 threads, one persistent CTA per SM):
 //   warps 0-3  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast) -> global
-//   warps 4-7  producer: global x rows -> hi/lo split -> 128B-swizzled K-major smem tiles
+//   warps 4-7  producer: TMA bulk copies of raw x rows (4-deep ring, one 12 KiB copy per tile) ->
+//              hi/lo split -> 128B-swizzled K-major smem tiles
 //   warp  8    TMEM allocator + single-thread UMMA issuer
 // Pipelines: smem stage full/empty mbarriers (producer <-> UMMA, freed by tcgen05.commit) and
 // TMEM stage full/empty mbarriers (UMMA <-> epilogue).
+#include <cstdlib>
+
 #include "mlp_kernels.cuh"
 #include "tc_common.cuh"
+
+// Debug timeline of CTA 0 (IMPALA_TC_TRACE=1), [tile < 24][event < 16]; see mlp_bwd_tc.cu.
+__device__ long long g_trace_fwd[24 * 16];
 
 namespace {
 
@@ -28,17 +34,20 @@ constexpr int kStages = 2;    // x tile stages in shared memory
 constexpr int kAccCols = 256; // TMEM columns per accumulator stage
 constexpr int kThreads = 9 * 32;
 constexpr int kTileBytes = kTileM * kKPad * 4;  // 16 KiB
+constexpr int kRawStages = 4;                   // bulk-copy ring depth
+constexpr int kRawStageBytes = kTileM * 28 * 4; // 14 KiB: 128 rows x O <= 28 floats
 
 struct FwdTcArgs {
     const float* x;
     const float* params;
     float* out;
     int M, O, H, N2, num_tiles;
+    int trace;
     MlpLayout lay;
 };
 
 struct __align__(8) Barriers {
-    uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    uint64_t raw_full[kRawStages], full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
@@ -52,10 +61,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     uint8_t* w_lo = w_hi + 256 * 128;
     uint8_t* x_hi = w_lo + 256 * 128;                       // kStages tiles
     uint8_t* x_lo = x_hi + kStages * kTileBytes;
-    float* w2s = reinterpret_cast<float*>(x_lo + kStages * kTileBytes);  // [H][NP]
+    uint8_t* raw = x_lo + kStages * kTileBytes;             // kRawStages x 14 KiB
+    float* w2s = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [H][NP]
     Barriers* bars = reinterpret_cast<Barriers*>(w2s + 256 * NP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ long long s_trace[24 * 16];
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8);
+#define TRACE(tile, ev)                                              \
+    if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
+    if (a.trace && blockIdx.x == 0)
+        for (int k = tid; k < 24 * 16; k += kThreads) s_trace[k] = 0;
+    TRACE(0, 15)
     const float* __restrict__ W1 = a.params + a.lay.oW1;
     const float* __restrict__ b1 = a.params + a.lay.ob1;
     const float* __restrict__ W2 = a.params + a.lay.oW2;
@@ -85,6 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     if (warp == 8) {
         tc::tmem_alloc(&bars->tmem_base, 512);
         if (lane == 0) {
+            for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
             for (int s = 0; s < kStages; ++s) {
                 tc::mbar_init(&bars->full[s], 4 * 32);  // every producer thread arrives
                 tc::mbar_init(&bars->empty[s], 1);      // tcgen05.commit
@@ -109,8 +127,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
         int it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1, aph = (it >> 1) & 1;
+            TRACE(it, 0)
             tc::mbar_wait(&bars->acc_full[as], aph);
             tc::tc_fence_after();
+            TRACE(it, 1)
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + as * kAccCols;
             float acc0[NP], acc1[NP];
 #pragma unroll
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             // all of this thread's TMEM reads are complete (wait::ld): release the stage
             tc::tc_fence_before();
             tc::mbar_arrive(&bars->acc_empty[as]);
+            TRACE(it, 2)
             const int row = tile * kTileM + 32 * warp + lane;
             if (row < a.M) {
                 if (NP == 4 && a.N2 == 4) {
@@ -153,22 +174,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
         }
     } else if (warp < 8) {
         // =============================== producer ===============================
-        const int r = 32 * (warp - 4) + lane;  // row of the tile this thread fills
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const int r = 32 * (warp - 4) + lane;  // row of the tile this thread converts
+        const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+        auto is_full = [&](int i) { return (tile_of(i) + 1) * kTileM <= a.M; };
+        auto issue_raw = [&](int i) {
+            if (warp == 4 && lane == 0 && is_full(i)) {
+                const int rs = i % kRawStages;
+                const uint32_t bytes = kTileM * O * 4;
+                tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
+                tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes);
+                tc::bulk_g2s(raw + rs * kRawStageBytes, a.x + (size_t)tile_of(i) * kTileM * O, bytes,
+                             &bars->raw_full[rs]);
+            }
+        };
+        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
+        for (int it = 0; it < n_my; ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
-            const int row = tile * kTileM + r;
-            const bool valid = row < a.M;
+            const int rs = it % kRawStages, rph = (it / kRawStages) & 1;
             float4 v[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid && c < ochunks)
-                    v[c] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)row * O) + c);
-                else if (c == ochunks)
-                    v[c].x = 1.f;  // the column that multiplies b1
+            for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            TRACE(it, 5)
+            if (is_full(it)) {
+                tc::mbar_wait(&bars->raw_full[rs], rph);
+                const float4* rx = reinterpret_cast<const float4*>(raw + rs * kRawStageBytes) + r * ochunks;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < ochunks) v[c] = rx[c];
+            } else {  // ragged last tile: plain guarded loads
+                const int row = tile_of(it) * kTileM + r;
+                if (row < a.M) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < ochunks) v[c] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)row * O) + c);
+                }
             }
+            TRACE(it, 6)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // all 4 producer warps drained the raw stage
+            if (it + kRawStages < n_my) issue_raw(it + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMAs that read this stage have retired
+            TRACE(it, 7)
             uint8_t* th = x_hi + s * kTileBytes;
             uint8_t* tl = x_lo + s * kTileBytes;
 #pragma unroll
@@ -184,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
+            TRACE(it, 8)
         }
     } else {
         // =============================== UMMA issuer ===============================
@@ -197,9 +247,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
             const int as = it & 1, aph = (it >> 1) & 1;
+            TRACE(it, 9)
             tc::mbar_wait(&bars->full[s], ph);
             tc::mbar_wait(&bars->acc_empty[as], aph ^ 1);
             tc::tc_fence_after();
+            TRACE(it, 10)
             if (tc::elect_one()) {
                 const uint32_t d = tmem_base + as * kAccCols;
                 const uint64_t so = static_cast<uint64_t>((s * kTileBytes) >> 4);
@@ -214,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
                 tc::umma_commit(&bars->acc_full[as]);  // accumulator ready for the epilogue
             }
             __syncwarp();
+            TRACE(it, 11)
         }
     }
 
@@ -223,10 +276,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    if (a.trace && blockIdx.x == 0) {
+        if (tid == 0) s_trace[1 * 16 + 15] = clock64();
+        __syncthreads();
+        for (int k = tid; k < 24 * 16; k += kThreads) g_trace_fwd[k] = s_trace[k];
+    }
+#undef TRACE
 }
 
 constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * 256 * 128 + 2 * kStages * kTileBytes +
-                              256 * 4 * sizeof(float) + sizeof(Barriers);
+                              kRawStages * kRawStageBytes + 256 * 4 * sizeof(float) + sizeof(Barriers);
 
 }  // namespace
 
@@ -243,6 +302,8 @@ int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, in
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
     a.num_tiles = (M + kTileM - 1) / kTileM;
     a.lay = impala_make_layout(O, H, N2);
+    const char* tr_env = std::getenv("IMPALA_TC_TRACE");
+    a.trace = tr_env && tr_env[0] == '1';
     static int sms = 0;
     static bool opted[2] = {false, false};
     cudaError_t e;
@@ -262,4 +323,12 @@ int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, in
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     return impala_launch_status();
+}
+
+// Debug only: the [24 tiles][16 events] clock stamps of the last traced forward launch (CTA 0).
+extern "C" int impala_debug_read_trace_fwd(long long* out, int n) {
+    cudaDeviceSynchronize();
+    if (n > 24 * 16) n = 24 * 16;
+    if (cudaMemcpyFromSymbol(out, g_trace_fwd, sizeof(long long) * n) != cudaSuccess) return -1;
+    return n;
 }
