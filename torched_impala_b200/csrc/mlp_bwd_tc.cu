@@ -100,20 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     TRACE(0, 15)
 
     // ---- one-time setup
-    for (int idx = tid; idx < H * 8; idx += kThreads) {
-        const int j = idx >> 3, c = idx & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ochunks) v = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
-        else if (c == ochunks) v.x = __ldg(b1 + j);
-        float4 hi, lo;
-        tc::split_tf32(v.x, hi.x, lo.x);
-        tc::split_tf32(v.y, hi.y, lo.y);
-        tc::split_tf32(v.z, hi.z, lo.z);
-        tc::split_tf32(v.w, hi.w, lo.w);
-        const uint32_t off = tc::sw128_offset(j, c);
-        *reinterpret_cast<float4*>(w_hi + off) = hi;
-        *reinterpret_cast<float4*>(w_lo + off) = lo;
-    }
+    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads);
     tc::fence_proxy_async();
     if (warp == 10) {
         tc::tmem_alloc(&bars->tmem_base, 512);

@@ -11,11 +11,13 @@
 // once: the epilogue thread that owns TMEM lane r applies ReLU and the tiny second layer
 // (<= 4 outputs) in registers and writes the row of logits / the value.
 //
-// Warp roles (288 threads, one persistent CTA per SM):
-//   warps 0-3  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast) -> global
-//   warps 4-7  producer: TMA bulk copies of raw x rows (4-deep ring, one 12 KiB copy per tile) ->
+// Warp roles (416 threads, one persistent CTA per SM):
+//   warps 0-7  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast) -> global; two
+//              warps per TMEM lane quarter, each taking half of the hidden columns (partial sums
+//              meet in shared memory)
+//   warps 8-11 producer: TMA bulk copies of raw x rows (4-deep ring, one 12 KiB copy per tile) ->
 //              hi/lo split -> 128B-swizzled K-major smem tiles
-//   warp  8    TMEM allocator + single-thread UMMA issuer
+//   warp  12   TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
 // Pipelines: smem stage full/empty mbarriers (producer <-> UMMA, freed by tcgen05.commit) and
 // TMEM stage full/empty mbarriers (UMMA <-> epilogue).
 #include <cstdlib>
@@ -32,7 +34,7 @@ constexpr int kTileM = 128;
 constexpr int kKPad = 32;     // floats per operand row = 128 bytes
 constexpr int kStages = 2;    // x tile stages in shared memory
 constexpr int kAccCols = 256; // TMEM columns per accumulator stage
-constexpr int kThreads = 9 * 32;
+constexpr int kThreads = 13 * 32;
 constexpr int kTileBytes = kTileM * kKPad * 4;  // 16 KiB
 constexpr int kRawStages = 4;                   // bulk-copy ring depth
 constexpr int kRawStageBytes = kTileM * 28 * 4; // 14 KiB: 128 rows x O <= 28 floats
@@ -63,11 +65,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     uint8_t* x_lo = x_hi + kStages * kTileBytes;
     uint8_t* raw = x_lo + kStages * kTileBytes;             // kRawStages x 14 KiB
     float* w2s = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [H][NP]
-    Barriers* bars = reinterpret_cast<Barriers*>(w2s + 256 * NP);
+    float* part = w2s + 256 * NP;                           // [2][128 rows][NP] partial sums of half 1
+    Barriers* bars = reinterpret_cast<Barriers*>(part + 2 * kTileM * NP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ long long s_trace[24 * 16];
-    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8);
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 12);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
     if (a.trace && blockIdx.x == 0)
@@ -80,26 +83,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     const int O = a.O, H = a.H, ochunks = O >> 2;
 
     // ---- one-time setup: W1' = [W1 | b1 | 0] split into hi/lo swizzled tiles, W2 transposed
-    for (int idx = tid; idx < H * 8; idx += kThreads) {
-        const int j = idx >> 3, c = idx & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ochunks) v = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
-        else if (c == ochunks) v.x = __ldg(b1 + j);
-        float4 hi, lo;
-        tc::split_tf32(v.x, hi.x, lo.x);
-        tc::split_tf32(v.y, hi.y, lo.y);
-        tc::split_tf32(v.z, hi.z, lo.z);
-        tc::split_tf32(v.w, hi.w, lo.w);
-        const uint32_t off = tc::sw128_offset(j, c);
-        *reinterpret_cast<float4*>(w_hi + off) = hi;
-        *reinterpret_cast<float4*>(w_lo + off) = lo;
-    }
+    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads);
     for (int idx = tid; idx < H * NP; idx += kThreads) {
         const int j = idx / NP, n = idx - j * NP;
         w2s[idx] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
     }
     tc::fence_proxy_async();
-    if (warp == 8) {
+    if (warp == 12) {
         tc::tmem_alloc(&bars->tmem_base, 512);
         if (lane == 0) {
             for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
@@ -109,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             }
             for (int s = 0; s < 2; ++s) {
                 tc::mbar_init(&bars->acc_full[s], 1);        // tcgen05.commit
-                tc::mbar_init(&bars->acc_empty[s], 4 * 32);  // every epilogue thread arrives
+                tc::mbar_init(&bars->acc_empty[s], 8 * 32);  // every epilogue thread arrives
             }
             tc::mbar_fence_init();
         }
@@ -119,11 +109,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =============================== epilogue ===============================
+        const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+        const int nch = H >> 5, nch0 = (nch + 1) >> 1;
+        const int cb_lo = half == 0 ? 0 : 32 * nch0, cb_hi = half == 0 ? 32 * nch0 : H;
         float b2r[NP];
 #pragma unroll
-        for (int n = 0; n < NP; ++n) b2r[n] = n < a.N2 ? __ldg(b2 + n) : 0.f;
+        for (int n = 0; n < NP; ++n) b2r[n] = (half == 0 && n < a.N2) ? __ldg(b2 + n) : 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1, aph = (it >> 1) & 1;
@@ -131,27 +124,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             tc::mbar_wait(&bars->acc_full[as], aph);
             tc::tc_fence_after();
             TRACE(it, 1)
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + as * kAccCols;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
             float acc0[NP], acc1[NP];
 #pragma unroll
             for (int n = 0; n < NP; ++n) acc0[n] = b2r[n], acc1[n] = 0.f;
-            for (int cb = 0; cb < H; cb += 32) {
-                float v[32];
-                tc::tmem_ld32(taddr + cb, v);
+            for (int cb = cb_lo; cb < cb_hi; cb += 64) {  // up to two 32-column loads in flight
+                uint32_t raw0[32], raw1[32];
+                const bool two = cb + 32 < cb_hi;
+                tc::tmem_ld32_nowait(taddr + cb, raw0);
+                if (two) tc::tmem_ld32_nowait(taddr + cb + 32, raw1);
+                tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float h0 = fmaxf(v[i], 0.f), h1 = fmaxf(v[i + 1], 0.f);
-                    if constexpr (NP == 4) {
-                        const float4 wa = *reinterpret_cast<const float4*>(w2s + (cb + i) * 4);
-                        const float4 wb = *reinterpret_cast<const float4*>(w2s + (cb + i + 1) * 4);
-                        acc0[0] = fmaf(h0, wa.x, acc0[0]), acc0[1] = fmaf(h0, wa.y, acc0[1]);
-                        acc0[2] = fmaf(h0, wa.z, acc0[2]), acc0[3] = fmaf(h0, wa.w, acc0[3]);
-                        acc1[0] = fmaf(h1, wb.x, acc1[0]), acc1[1] = fmaf(h1, wb.y, acc1[1]);
-                        acc1[2] = fmaf(h1, wb.z, acc1[2]), acc1[3] = fmaf(h1, wb.w, acc1[3]);
-                    } else {
-                        const float2 w = *reinterpret_cast<const float2*>(w2s + cb + i);
-                        acc0[0] = fmaf(h0, w.x, acc0[0]);
-                        acc1[0] = fmaf(h1, w.y, acc1[0]);
+                for (int hb = 0; hb < 2; ++hb) {
+                    if (hb == 1 && !two) break;
+                    const int c0 = cb + 32 * hb;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float h0 = fmaxf(__uint_as_float(hb ? raw1[i] : raw0[i]), 0.f);
+                        const float h1 = fmaxf(__uint_as_float(hb ? raw1[i + 1] : raw0[i + 1]), 0.f);
+                        if constexpr (NP == 4) {
+                            const float4 wa = *reinterpret_cast<const float4*>(w2s + (c0 + i) * 4);
+                            const float4 wb = *reinterpret_cast<const float4*>(w2s + (c0 + i + 1) * 4);
+                            acc0[0] = fmaf(h0, wa.x, acc0[0]), acc0[1] = fmaf(h0, wa.y, acc0[1]);
+                            acc0[2] = fmaf(h0, wa.z, acc0[2]), acc0[3] = fmaf(h0, wa.w, acc0[3]);
+                            acc1[0] = fmaf(h1, wb.x, acc1[0]), acc1[1] = fmaf(h1, wb.y, acc1[1]);
+                            acc1[2] = fmaf(h1, wb.z, acc1[2]), acc1[3] = fmaf(h1, wb.w, acc1[3]);
+                        } else {
+                            const float2 w = *reinterpret_cast<const float2*>(w2s + c0 + i);
+                            acc0[0] = fmaf(h0, w.x, acc0[0]);
+                            acc1[0] = fmaf(h1, w.y, acc1[0]);
+                        }
                     }
                 }
             }
@@ -159,27 +161,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
             tc::tc_fence_before();
             tc::mbar_arrive(&bars->acc_empty[as]);
             TRACE(it, 2)
-            const int row = tile * kTileM + 32 * warp + lane;
-            if (row < a.M) {
+            const int rl = 32 * q + lane;  // row of the tile
+            float* pbuf = part + ((it & 1) * kTileM + rl) * NP;
+            if (half == 1) {
+#pragma unroll
+                for (int n = 0; n < NP; ++n) pbuf[n] = acc0[n] + acc1[n];
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");  // the two column halves meet
+            const int row = tile * kTileM + rl;
+            if (half == 0 && row < a.M) {
                 if (NP == 4 && a.N2 == 4) {
+                    const float4 o = *reinterpret_cast<const float4*>(pbuf);
                     *reinterpret_cast<float4*>(a.out + (size_t)row * 4) =
-                        make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2],
-                                    acc0[3] + acc1[3]);
+                        make_float4(acc0[0] + acc1[0] + o.x, acc0[1] + acc1[1] + o.y,
+                                    acc0[2] + acc1[2] + o.z, acc0[3] + acc1[3] + o.w);
                 } else {
 #pragma unroll
                     for (int n = 0; n < NP; ++n)
-                        if (n < a.N2) a.out[(size_t)row * a.N2 + n] = acc0[n] + acc1[n];
+                        if (n < a.N2) a.out[(size_t)row * a.N2 + n] = acc0[n] + acc1[n] + pbuf[n];
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // =============================== producer ===============================
-        const int r = 32 * (warp - 4) + lane;  // row of the tile this thread converts
+        const int r = 32 * (warp - 8) + lane;  // row of the tile this thread converts
         const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kTileM <= a.M; };
         auto issue_raw = [&](int i) {
-            if (warp == 4 && lane == 0 && is_full(i)) {
+            if (warp == 8 && lane == 0 && is_full(i)) {
                 const int rs = i % kRawStages;
                 const uint32_t bytes = kTileM * O * 4;
                 tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
 }
 
 constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * 256 * 128 + 2 * kStages * kTileBytes +
-                              kRawStages * kRawStageBytes + 256 * 4 * sizeof(float) + sizeof(Barriers);
+                              kRawStages * kRawStageBytes + (256 + 2 * kTileM) * 4 * sizeof(float) + sizeof(Barriers);
 
 }  // namespace
 

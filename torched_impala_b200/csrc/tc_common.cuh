@@ -133,6 +133,24 @@ __device__ __forceinline__ void tmem_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// same without the wait, so several loads can be in flight; follow with tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31},"
+        "[%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ UMMA
 // K-major operand tile, rows of 128 bytes (32 tf32), SWIZZLE_128B, 8-row groups 1024 B apart.
 // `byte_off` selects the K step inside the 128-byte row (32 bytes per K=8 step).
@@ -201,6 +219,42 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // byte offset of 16-byte chunk `c16` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c16) {
     return (r >> 3) * 1024u + (r & 7u) * 128u + ((c16 ^ (r & 7u)) << 4);
+}
+
+// W1' = [W1 | b1 | 0] (H rows x 32 floats) split into tf32 hi / lo K-major SWIZZLE_128B tiles.
+// All global loads of a thread are issued before the first conversion so their latencies overlap
+// (the rows are L2-resident parameters; a load -> convert -> store loop would serialise ~8 round
+// trips).  nthreads <= 8 * 256 / MAXIT must hold for H <= 256: MAXIT = 8 covers >= 256 threads.
+__device__ __forceinline__ void stage_w1_tiles(uint8_t* w_hi, uint8_t* w_lo, const float* __restrict__ W1,
+                                               const float* __restrict__ b1, int H, int O, int tid,
+                                               int nthreads) {
+    constexpr int MAXIT = 8;
+    const int ochunks = O >> 2;
+    float4 v[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int idx = tid + it * nthreads;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < H * 8) {
+            const int j = idx >> 3, c = idx & 7;
+            if (c < ochunks) v[it] = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
+            else if (c == ochunks) v[it].x = __ldg(b1 + j);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int idx = tid + it * nthreads;
+        if (idx < H * 8) {
+            float4 hi, lo;
+            split_tf32(v[it].x, hi.x, lo.x);
+            split_tf32(v[it].y, hi.y, lo.y);
+            split_tf32(v[it].z, hi.z, lo.z);
+            split_tf32(v[it].w, hi.w, lo.w);
+            const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+            *reinterpret_cast<float4*>(w_hi + off) = hi;
+            *reinterpret_cast<float4*>(w_lo + off) = lo;
+        }
+    }
 }
 
 }  // namespace tc
