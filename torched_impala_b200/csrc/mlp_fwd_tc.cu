@@ -56,8 +56,9 @@ struct __align__(8) Barriers {
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(FwdTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by OFFSETTING the __shared__ array (a round trip through an integer
+    // would make every derived pointer generic: LD/ST instead of LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     // carve-up (all tile bases 1024-byte aligned for SWIZZLE_128B)
     uint8_t* w_hi = smem;                                   // [H rows][128 B]  (<= 32 KiB)
     uint8_t* w_lo = w_hi + 256 * 128;
