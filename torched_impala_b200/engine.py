@@ -124,8 +124,6 @@ class LearnerEngine:
         self._ticket = 0
 
         self._graph_main = [None] * slabs
-        self._graph_full = [None] * slabs  # N > 1: kernels + all-reduce + optimizer in one graph
-        self._fused_ok = True
         self._graph_opt = None
         self.steps_done = 0
 
@@ -246,19 +244,6 @@ class LearnerEngine:
 
     def _capture(self, slot: int):
         with torch.cuda.stream(self.stream):
-            if self.world > 1 and self._fused_ok:
-                # whole step (kernels + NCCL all-reduce + optimizer) as ONE graph launch per step
-                try:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=self.stream):
-                        self._enqueue_main(slot)
-                        self._all_reduce()
-                        self._enqueue_opt()
-                    self._graph_full[slot] = g
-                    return
-                except Exception as e:  # NCCL build without capture support: keep the 3-part path
-                    print(f"[engine] fused graph capture failed ({e!r}); using split graphs")
-                    self._fused_ok = False
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, stream=self.stream):
                 self._enqueue_main(slot)
@@ -269,25 +254,13 @@ class LearnerEngine:
                     self._enqueue_opt()
                 self._graph_opt = g2
 
-    def _all_reduce(self):
-        import torch.distributed as dist
-
-        dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)
-
     def step(self, slot: int = 0) -> None:
         """One learner update on the batch in device slab `slot` (async on `self.stream`)."""
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.slab_ready[slot])
             if self.use_graph and self.steps_done >= 1:
-                if self._graph_main[slot] is None and self._graph_full[slot] is None:
+                if self._graph_main[slot] is None:
                     self._capture(slot)
-                if self._graph_full[slot] is not None:
-                    self._graph_full[slot].replay()
-                    self.slab_free[slot].record(self.stream)
-                    self._slab_used[slot] = True
-                    self.launches_per_step = 8
-                    self.steps_done += 1
-                    return
                 self._graph_main[slot].replay()
                 n = 7
             else:
@@ -295,7 +268,9 @@ class LearnerEngine:
             self.slab_free[slot].record(self.stream)
             self._slab_used[slot] = True
             if self.world > 1:
-                self._all_reduce()
+                import torch.distributed as dist
+
+                dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)
             if self.use_graph and self._graph_opt is not None:
                 self._graph_opt.replay()
                 n += 1
