@@ -19,6 +19,6 @@ def test_two_rank_nccl_matches_single_gpu():
     script = os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), script],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout
