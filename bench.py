@@ -41,8 +41,8 @@ def peaks():
         with open(p) as f:
             d = json.load(f)
         return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)),
-                    source="MEASURED_PEAKS.json (measured)")
-    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+                    bf16_tflops=float(d.get("bf16_tflops", 1590.0)), source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
 
 
 def hparams(B):
@@ -358,13 +358,27 @@ def run_own_arm(args):
         kern = kernel_breakdown(eng, flush)
     pk = peaks()
     fp32_peak = SMS * FP32_LANES * 2 * pk["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at max SM clock
+    tf32_peak = pk["bf16_tflops"] / 2.0  # tf32 UMMA rate = half the (measured) bf16 rate
+    H, O, A = eng.H_pi, eng.O, eng.A
+    on_tc = (os.environ.get("IMPALA_MLP_TC", "1") != "0" and O % 4 == 0 and 4 <= O <= 28
+             and H in (128, 256) and A <= 4)
+    # tensor-core work actually issued: 3xTF32 (3 UMMAs per product), K padded to 32, and the
+    # backward runs two GEMMs per row (recompute + dW1 reduction)
+    executed = {"mlp_forward(policy)": 2.0 * eng.M_pi * H * 32 * 3, "mlp_forward(value_fn)": 2.0 * eng.M_vf * H * 32 * 3,
+                "mlp_backward(policy)": 2.0 * eng.M_pi * H * 32 * 6, "mlp_backward(value_fn)": 2.0 * eng.M_vf * H * 32 * 6}
     kernels = {}
     for name, k in kern.items():
         ent = dict(us=round(k["us"], 3))
         if k["flops"]:
             ach = k["flops"] / (k["us"] * 1e-6) / 1e12
-            ent.update(bound="fp32", achieved=round(ach, 3), peak=round(fp32_peak, 2), unit="TFLOP/s",
-                       frac=round(ach / fp32_peak, 4))
+            if on_tc:
+                ex = executed[name] / (k["us"] * 1e-6) / 1e12
+                ent.update(bound="tensor", achieved=round(ach, 3), peak=round(tf32_peak, 1), unit="TFLOP/s",
+                           frac=round(ach / tf32_peak, 4), executed_tflops=round(ex, 1),
+                           executed_frac=round(ex / tf32_peak, 4))
+            else:
+                ent.update(bound="fp32", achieved=round(ach, 3), peak=round(fp32_peak, 2), unit="TFLOP/s",
+                           frac=round(ach / fp32_peak, 4))
         else:
             ach = k["bytes"] / (k["us"] * 1e-6) / 1e9
             ent.update(bound="hbm", achieved=round(ach, 1), peak=pk["hbm_gbs"], unit="GB/s",
@@ -376,11 +390,13 @@ def run_own_arm(args):
     if os.path.exists(prof):
         with open(prof) as f:
             traffic = json.load(f).get(dom)
-    roofline = dict(kernel=dom, traffic=traffic,
-                    peak_source=(pk["source"] if kernels[dom]["bound"] == "hbm" else
-                                 f"148 SMs x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (max SM clock, "
-                                 f"{pk['source']}); MEASURED_PEAKS has no FP32 figure"),
-                    **{k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")})
+    src = {"hbm": pk["source"],
+           "tensor": f"tf32 UMMA peak = measured bf16 {pk['bf16_tflops']:.1f} TF/s / 2 ({pk['source']}); `achieved` counts "
+                     "ALGORITHMIC fp32 FLOPs (SURVEY 8d), `executed_tflops` the 3xTF32 / K-padded / recompute work issued",
+           "fp32": f"148 SMs x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz (max SM clock, {pk['source']}); "
+                   "MEASURED_PEAKS has no FP32 figure"}[kernels[dom]["bound"]]
+    roofline = dict(kernel=dom, traffic=traffic, peak_source=src,
+                    **{k: kernels[dom][k] for k in kernels[dom] if k != "us"})
 
     if world > 1:
         import torch.distributed as dist
