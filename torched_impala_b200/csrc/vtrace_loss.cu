@@ -23,6 +23,8 @@
 // i.e. the affine map F_i(x) = (delta_i - g_i v_{i+1}) + g_i x with g_i = disc_i c_i.
 #include <math.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -373,6 +375,252 @@ __global__ void __launch_bounds__(kThreads, 3) vtrace_kernel(VtArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for A == 4 and B % 8 == 0 (the benchmark shapes): same algorithm, but the unroll is
+// walked in 32-step chunks through a 3-stage cp.async pipeline, so every CTA always has the
+// next two chunks of its five input tensors in flight while one warp-pass of math runs -
+// the stand-alone scan is HBM-latency bound otherwise (one CTA = 8 trajectories = ~36 KB of
+// loads per 100 steps).  Logits live in shared memory as float4 with an XOR swizzle
+// ([tt][w ^ (tt & 7)]): 16-byte cp.async in, conflict-free 128-bit column reads out.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFStages = 3;
+
+struct __align__(16) FastStage {
+    float4 cur[32 * kTraj];
+    float4 beh[32 * kTraj];
+    float v[33 * kColStride + 3];
+    float r[32 * kColStride];
+    int act[32 * kColStride];
+    uint2 done[32];
+};
+struct __align__(16) FastOut {
+    float4 dl[32 * kTraj];
+    float vs[33 * kColStride + 3];
+    float dv[33 * kColStride + 3];
+    float pg[32 * kColStride];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const unsigned n = valid ? 16u : 0u;  // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+    const unsigned n = valid ? 8u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+    const unsigned n = valid ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(n) : "memory");
+}
+
+template <bool WITH_LOSS>
+__global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
+    extern __shared__ __align__(16) unsigned char fsmem[];
+    FastStage* stages = reinterpret_cast<FastStage*>(fsmem);
+    FastOut* out = reinterpret_cast<FastOut*>(fsmem + kFStages * sizeof(FastStage));
+    __shared__ double s_red[kTraj][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int T = a.T, B = a.B;
+    const int b0 = blockIdx.x * kTraj, b = b0 + w;
+    const int L = min(max(__ldg(a.lens + b), 0), T);
+    const float v0 = __ldg(a.v + b);  // V(x_0): the reference's v[:1]
+    const int nch = (T + 31) >> 5;
+
+    auto issue_chunk = [&](int c, int stg) {
+        FastStage& st = stages[stg];
+        const int t0 = c * 32;
+        {
+            const int tt = tid >> 3, col = tid & 7, t = t0 + tt;
+            const bool ok = t < T;
+            const size_t g = ok ? ((size_t)t * B + b0 + col) : 0;
+            const int slot = tt * kTraj + (col ^ (tt & 7));
+            cp_async16(&st.cur[slot], a.cur_logits + g * 4, ok);
+            cp_async16(&st.beh[slot], a.beh_logits + g * 4, ok);
+            cp_async4(&st.r[tt * kColStride + col], a.rewards + g, ok);
+            cp_async4(&st.act[tt * kColStride + col], a.actions + g, ok);
+            const bool okv = t <= T;
+            cp_async4(&st.v[tt * kColStride + col], a.v + (okv ? ((size_t)t * B + b0 + col) : 0), okv);
+        }
+        if (tid < kTraj) {  // 33rd row of v (first row of the chunk processed before this one)
+            const int t = t0 + 32;
+            const bool okv = t <= T;
+            cp_async4(&st.v[32 * kColStride + tid], a.v + (okv ? ((size_t)t * B + b0 + tid) : 0), okv);
+        } else if (tid >= 32 && tid < 64) {
+            const int tt = tid - 32, t = t0 + tt;
+            const bool ok = t < T;
+            cp_async8(&st.done[tt], a.done + (ok ? ((size_t)t * B + b0) : 0), ok);
+        }
+    };
+
+    for (int k = 0; k < kFStages - 1; ++k) {
+        if (nch - 1 - k >= 0) issue_chunk(nch - 1 - k, k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    double sum_vl = 0.0, sum_pl = 0.0, sum_ent = 0.0, sum_rw = 0.0;
+    float carry = 0.f;  // acc at the first index after the current chunk
+    for (int ci = 0; ci < nch; ++ci) {
+        const int c = nch - 1 - ci, t0 = c * 32;
+        asm volatile("cp.async.wait_group %0;" ::"n"(kFStages - 2) : "memory");
+        __syncthreads();  // chunk c is in shared memory; the out tile and stage (ci-1)%S are free
+        {
+            const int cn = c - (kFStages - 1);
+            if (cn >= 0) issue_chunk(cn, (ci + kFStages - 1) % kFStages);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const FastStage& st = stages[ci % kFStages];
+        {
+            const int tt = lane, t = t0 + tt;
+            const bool valid = t < L;
+            const float r = st.r[tt * kColStride + w];
+            const int act = st.act[tt * kColStride + w];
+            const bool dn = (reinterpret_cast<const unsigned char*>(&st.done[tt]))[w] != 0;
+            const float v_t = st.v[tt * kColStride + w];
+            const float v_n = st.v[(tt + 1) * kColStride + w];
+            const int slot = tt * kTraj + (w ^ (tt & 7));
+            const float4 zc = st.cur[slot], zbv = st.beh[slot];
+            const float z[4] = {zc.x, zc.y, zc.z, zc.w}, zb[4] = {zbv.x, zbv.y, zbv.z, zbv.w};
+            const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+            const float mxb = fmaxf(fmaxf(zb[0], zb[1]), fmaxf(zb[2], zb[3]));
+            const float se = (__expf(z[0] - mx) + __expf(z[1] - mx)) + (__expf(z[2] - mx) + __expf(z[3] - mx));
+            const float seb = (__expf(zb[0] - mxb) + __expf(zb[1] - mxb)) + (__expf(zb[2] - mxb) + __expf(zb[3] - mxb));
+            const float lse = mx + __logf(se), lseb = mxb + __logf(seb);
+            const float z_a = act == 1 ? z[1] : (act == 2 ? z[2] : (act == 3 ? z[3] : z[0]));
+            const float zb_a = act == 1 ? zb[1] : (act == 2 ? zb[2] : (act == 3 ? zb[3] : zb[0]));
+            const float lp_cur = z_a - lse, lp_beh = zb_a - lseb;
+            const float ratio = __expf(lp_cur - lp_beh);                   // :121-123
+            const float rho = valid ? fminf(ratio, a.rho_bar) : 0.f;       // :124
+            const float cc = valid ? fminf(ratio, a.c_bar) : 0.f;          // :125
+            const float disc = (valid && !dn) ? a.gamma : 0.f;             // :109
+            const float g = disc * cc;
+            float fa;  // affine map F(x) = fa + g x
+            if (a.mode == IMPALA_MODE_REFERENCE) {
+                const float delta = rho * (r + a.gamma * v_n - v0);        // :126
+                fa = delta - g * v_n;                                      // :130
+            } else {
+                fa = rho * (r + disc * v_n - v_t);
+            }
+            float sa = fa, sg = g;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float a2 = __shfl_down_sync(IMPALA_FULL_MASK, sa, off);
+                const float g2 = __shfl_down_sync(IMPALA_FULL_MASK, sg, off);
+                if (lane + off < 32) {
+                    sa = fmaf(sg, a2, sa);
+                    sg = sg * g2;
+                }
+            }
+            const float acc_t = fmaf(sg, carry, sa);
+            float acc_n = __shfl_down_sync(IMPALA_FULL_MASK, acc_t, 1);
+            if (lane == 31) acc_n = carry;
+            carry = __shfl_sync(IMPALA_FULL_MASK, acc_t, 0);
+            const float vs_n = acc_n + v_n;                                // :131
+            const float pg = rho * (r + disc * vs_n - v_t);                // :135
+            out->vs[tt * kColStride + w] = (t <= L) ? acc_t + v_t : 0.f;
+            out->pg[tt * kColStride + w] = pg;  // rho == 0 on padding
+            if (WITH_LOSS) {
+                out->dv[tt * kColStride + w] = valid ? -a.v_loss_c * a.inv_batch * acc_t : 0.f;
+                float lz[4], pk[4], ent = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lz[k] = z[k] - lse;
+                    pk[k] = __expf(lz[k]);
+                    ent -= pk[k] * lz[k];                                  // :310-314, :153
+                }
+                float dz[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float onehot = (k == act) ? 1.f : 0.f;
+                    const float d = a.inv_batch * (a.policy_loss_c * pg * (pk[k] - onehot) +
+                                                   a.entropy_c * pk[k] * (lz[k] + ent));
+                    dz[k] = valid ? d : 0.f;
+                }
+                out->dl[slot] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+                if (valid) {
+                    sum_vl += 0.5 * (double)acc_t * (double)acc_t;
+                    sum_pl += (double)(-lp_cur * pg);                      // :317-321
+                    sum_ent += (double)ent;
+                    sum_rw += (double)r;                                   // :108
+                }
+            }
+            // bootstrap row T when it is exactly the extra (33rd) row of the last chunk
+            if (ci == 0 && t0 + 32 == T && lane == 0) {
+                out->vs[32 * kColStride + w] = (L == T) ? st.v[32 * kColStride + w] : 0.f;
+                if (WITH_LOSS) out->dv[32 * kColStride + w] = 0.f;
+            }
+        }
+        __syncthreads();
+        // ---- row-contiguous 128-bit stores of this chunk's outputs
+        const int rows_v = (ci == 0 && t0 + 32 == T) ? 33 : 32;
+        if (tid < rows_v * 2) {
+            const int tt = tid >> 1, h = tid & 1, t = t0 + tt;
+            if (t <= T) {
+                const size_t g = (size_t)t * B + b0;
+                const float* sv = out->vs + tt * kColStride + 4 * h;
+                reinterpret_cast<float4*>(a.vs + g)[h] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                if (WITH_LOSS) {
+                    const float* sd = out->dv + tt * kColStride + 4 * h;
+                    reinterpret_cast<float4*>(a.dv + g)[h] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+                }
+            }
+        } else if (tid >= 128 && tid < 192 && a.pg_adv) {
+            const int idx = tid - 128, tt = idx >> 1, h = idx & 1, t = t0 + tt;
+            if (t < T) {
+                const float* sp = out->pg + tt * kColStride + 4 * h;
+                reinterpret_cast<float4*>(a.pg_adv + (size_t)t * B + b0)[h] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+        }
+        if (WITH_LOSS) {
+            const int tt = tid >> 3, col = tid & 7, t = t0 + tt;
+            if (t < T)
+                reinterpret_cast<float4*>(a.dlogits)[(size_t)t * B + b0 + col] = out->dl[tt * kTraj + (col ^ (tt & 7))];
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    if (WITH_LOSS) {
+        __shared__ bool s_last;
+        __shared__ double s_fin[64][4];
+        sum_vl = warp_sum_f64(sum_vl);
+        sum_pl = warp_sum_f64(sum_pl);
+        sum_ent = warp_sum_f64(sum_ent);
+        sum_rw = warp_sum_f64(sum_rw);
+        if (lane == 0) {
+            s_red[w][0] = sum_vl, s_red[w][1] = sum_pl, s_red[w][2] = sum_ent, s_red[w][3] = sum_rw;
+        }
+        __syncthreads();
+        if (tid < 4) {
+            double s = 0.0;
+            for (int i = 0; i < kTraj; ++i) s += s_red[i][tid];
+            a.partials[(size_t)blockIdx.x * 4 + tid] = s;
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int which = tid & 3, stripe = tid >> 2;
+            double s = 0.0;
+            for (unsigned cta = stripe; cta < gridDim.x; cta += 64)
+                s += __ldcg(a.partials + (size_t)cta * 4 + which);
+            s_fin[stripe][which] = s;
+            __syncthreads();
+            if (tid < 4) {
+                double tot = 0.0;
+                for (int i = 0; i < 64; ++i) tot += s_fin[i][tid];
+                a.scalars[tid] = tot * (double)a.inv_batch;
+            }
+            if (tid == 0) *a.counter = 0u;
+        }
+    }
+}
+
 int pick_ap(int A) {
     if (A <= 2) return 2;
     if (A <= 4) return 4;
@@ -403,6 +651,14 @@ int launch(VtArgs& a, cudaStream_t st) {
                      aligned16(a.actions) && aligned16(a.rewards) && aligned16(a.v) &&
                      aligned16(a.vs) && aligned16(a.pg_adv) && aligned16(a.dlogits) &&
                      aligned16(a.dv) && (reinterpret_cast<uintptr_t>(a.done) & 3) == 0;
+    {
+        const char* fenv = std::getenv("IMPALA_VTRACE_FAST");
+        if (vec && a.A == 4 && (reinterpret_cast<uintptr_t>(a.done) & 7) == 0 && !(fenv && fenv[0] == '0')) {
+            const size_t fsmem = kFStages * sizeof(FastStage) + sizeof(FastOut);
+            vtrace_fast_kernel<WITH_LOSS><<<grid, kThreads, fsmem, st>>>(a);
+            return impala_launch_status();
+        }
+    }
 #define VT_LAUNCH(APV)                                   \
     if (vec && a.A == APV) VT_LAUNCH_V(APV, true, true)  \
     else if (vec) VT_LAUNCH_V(APV, true, false)          \
