@@ -431,36 +431,57 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
     const float v0 = __ldg(a.v + b);  // V(x_0): the reference's v[:1]
     const int nch = (T + 31) >> 5;
 
+    // Staging role of this thread (fixed for the kernel): time row ltt, column lcol of every chunk.
+    // Global pointers are set to the LAST chunk and bumped backwards by 32 rows per chunk, so the
+    // steady state issues its cp.asyncs without any 64-bit index arithmetic.
+    const int ltt = tid >> 3, lcol = tid & 7;
+    const int lslot = ltt * kTraj + (lcol ^ (ltt & 7));
+    const int lrow9 = ltt * kColStride + lcol;
+    const size_t lrow = (size_t)((nch - 1) * 32 + ltt) * B + b0 + lcol;  // element (t, b0 + lcol)
+    const float4* p_cur = reinterpret_cast<const float4*>(a.cur_logits) + lrow;
+    const float4* p_beh = reinterpret_cast<const float4*>(a.beh_logits) + lrow;
+    const float* p_r = a.rewards + lrow;
+    const int32_t* p_act = a.actions + lrow;
+    const float* p_v = a.v + lrow;
+    const float* p_v33 = a.v + (size_t)(nch * 32) * B + b0 + (tid & 7);       // threads 0..7
+    const uint8_t* p_done = a.done + (size_t)((nch - 1) * 32 + (tid & 31)) * B + b0;  // threads 32..63
+    const ptrdiff_t step = (ptrdiff_t)32 * B;  // elements per 32 time steps
+
     auto issue_chunk = [&](int c, int stg) {
         FastStage& st = stages[stg];
-        const int t0 = c * 32;
-        {
-            const int tt = tid >> 3, col = tid & 7, t = t0 + tt;
-            const bool ok = t < T;
-            const size_t g = ok ? ((size_t)t * B + b0 + col) : 0;
-            const int slot = tt * kTraj + (col ^ (tt & 7));
-            cp_async16(&st.cur[slot], a.cur_logits + g * 4, ok);
-            cp_async16(&st.beh[slot], a.beh_logits + g * 4, ok);
-            cp_async4(&st.r[tt * kColStride + col], a.rewards + g, ok);
-            cp_async4(&st.act[tt * kColStride + col], a.actions + g, ok);
-            const bool okv = t <= T;
-            cp_async4(&st.v[tt * kColStride + col], a.v + (okv ? ((size_t)t * B + b0 + col) : 0), okv);
-        }
+        // only the last chunk can reach past the end of the unroll
+        const int t = c * 32 + ltt;
+        const bool ok = t < T, okv = t <= T;
+        cp_async16(&st.cur[lslot], ok ? p_cur : reinterpret_cast<const float4*>(a.cur_logits), ok);
+        cp_async16(&st.beh[lslot], ok ? p_beh : reinterpret_cast<const float4*>(a.beh_logits), ok);
+        cp_async4(&st.r[lrow9], ok ? p_r : a.rewards, ok);
+        cp_async4(&st.act[lrow9], ok ? p_act : a.actions, ok);
+        cp_async4(&st.v[lrow9], okv ? p_v : a.v, okv);
         if (tid < kTraj) {  // 33rd row of v (first row of the chunk processed before this one)
-            const int t = t0 + 32;
-            const bool okv = t <= T;
-            cp_async4(&st.v[32 * kColStride + tid], a.v + (okv ? ((size_t)t * B + b0 + tid) : 0), okv);
+            const bool ok33 = c * 32 + 32 <= T;
+            cp_async4(&st.v[32 * kColStride + tid], ok33 ? p_v33 : a.v, ok33);
         } else if (tid >= 32 && tid < 64) {
-            const int tt = tid - 32, t = t0 + tt;
-            const bool ok = t < T;
-            cp_async8(&st.done[tt], a.done + (ok ? ((size_t)t * B + b0) : 0), ok);
+            const bool okd = c * 32 + (tid - 32) < T;
+            cp_async8(&st.done[tid - 32], okd ? p_done : a.done, okd);
         }
+        p_cur -= step, p_beh -= step, p_r -= step, p_act -= step, p_v -= step, p_v33 -= step, p_done -= step;
     };
 
     for (int k = 0; k < kFStages - 1; ++k) {
         if (nch - 1 - k >= 0) issue_chunk(nch - 1 - k, k);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+
+    // compute role: lane = time step inside the chunk, warp = trajectory
+    const int crow9 = lane * kColStride + w, cslot = lane * kTraj + (w ^ (lane & 7));
+    int stg_c = 0, stg_n = kFStages - 1;  // stage being consumed / stage being refilled
+    // output pointers of this thread's store roles, bumped backwards like the inputs
+    const int s_tt = tid >> 1, s_h = tid & 1;  // vs / dv: threads 0..65
+    float* q_vs = a.vs + (size_t)((nch - 1) * 32 + s_tt) * B + b0 + 4 * s_h;
+    float* q_dv = WITH_LOSS ? a.dv + (size_t)((nch - 1) * 32 + s_tt) * B + b0 + 4 * s_h : nullptr;
+    const int p_tt = (tid - 128) >> 1, p_h = tid & 1;  // pg: threads 128..191
+    float* q_pg = a.pg_adv ? a.pg_adv + (size_t)((nch - 1) * 32 + p_tt) * B + b0 + 4 * p_h : nullptr;
+    float4* q_dl = WITH_LOSS ? reinterpret_cast<float4*>(a.dlogits) + lrow : nullptr;
 
     double sum_vl = 0.0, sum_pl = 0.0, sum_ent = 0.0, sum_rw = 0.0;
     float carry = 0.f;  // acc at the first index after the current chunk
@@ -470,19 +491,21 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
         __syncthreads();  // chunk c is in shared memory; the out tile and stage (ci-1)%S are free
         {
             const int cn = c - (kFStages - 1);
-            if (cn >= 0) issue_chunk(cn, (ci + kFStages - 1) % kFStages);
+            if (cn >= 0) issue_chunk(cn, stg_n);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const FastStage& st = stages[ci % kFStages];
+        const FastStage& st = stages[stg_c];
+        stg_n = stg_c;
+        stg_c = stg_c + 1 == kFStages ? 0 : stg_c + 1;
         {
             const int tt = lane, t = t0 + tt;
             const bool valid = t < L;
-            const float r = st.r[tt * kColStride + w];
-            const int act = st.act[tt * kColStride + w];
+            const float r = st.r[crow9];
+            const int act = st.act[crow9];
             const bool dn = (reinterpret_cast<const unsigned char*>(&st.done[tt]))[w] != 0;
-            const float v_t = st.v[tt * kColStride + w];
-            const float v_n = st.v[(tt + 1) * kColStride + w];
-            const int slot = tt * kTraj + (w ^ (tt & 7));
+            const float v_t = st.v[crow9];
+            const float v_n = st.v[crow9 + kColStride];
+            const int slot = cslot;
             const float4 zc = st.cur[slot], zbv = st.beh[slot];
             const float z[4] = {zc.x, zc.y, zc.z, zc.w}, zb[4] = {zbv.x, zbv.y, zbv.z, zbv.w};
             const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
@@ -521,10 +544,10 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
             carry = __shfl_sync(IMPALA_FULL_MASK, acc_t, 0);
             const float vs_n = acc_n + v_n;                                // :131
             const float pg = rho * (r + disc * vs_n - v_t);                // :135
-            out->vs[tt * kColStride + w] = (t <= L) ? acc_t + v_t : 0.f;
-            out->pg[tt * kColStride + w] = pg;  // rho == 0 on padding
+            out->vs[crow9] = (t <= L) ? acc_t + v_t : 0.f;
+            out->pg[crow9] = pg;  // rho == 0 on padding
             if (WITH_LOSS) {
-                out->dv[tt * kColStride + w] = valid ? -a.v_loss_c * a.inv_batch * acc_t : 0.f;
+                out->dv[crow9] = valid ? -a.v_loss_c * a.inv_batch * acc_t : 0.f;
                 float lz[4], pk[4], ent = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -558,28 +581,27 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
         // ---- row-contiguous 128-bit stores of this chunk's outputs
         const int rows_v = (ci == 0 && t0 + 32 == T) ? 33 : 32;
         if (tid < rows_v * 2) {
-            const int tt = tid >> 1, h = tid & 1, t = t0 + tt;
-            if (t <= T) {
-                const size_t g = (size_t)t * B + b0;
-                const float* sv = out->vs + tt * kColStride + 4 * h;
-                reinterpret_cast<float4*>(a.vs + g)[h] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            if (t0 + s_tt <= T) {
+                const float* sv = out->vs + s_tt * kColStride + 4 * s_h;
+                *reinterpret_cast<float4*>(q_vs) = make_float4(sv[0], sv[1], sv[2], sv[3]);
                 if (WITH_LOSS) {
-                    const float* sd = out->dv + tt * kColStride + 4 * h;
-                    reinterpret_cast<float4*>(a.dv + g)[h] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+                    const float* sd = out->dv + s_tt * kColStride + 4 * s_h;
+                    *reinterpret_cast<float4*>(q_dv) = make_float4(sd[0], sd[1], sd[2], sd[3]);
                 }
             }
-        } else if (tid >= 128 && tid < 192 && a.pg_adv) {
-            const int idx = tid - 128, tt = idx >> 1, h = idx & 1, t = t0 + tt;
-            if (t < T) {
-                const float* sp = out->pg + tt * kColStride + 4 * h;
-                reinterpret_cast<float4*>(a.pg_adv + (size_t)t * B + b0)[h] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        } else if (tid >= 128 && tid < 192 && q_pg) {
+            if (t0 + p_tt < T) {
+                const float* sp = out->pg + p_tt * kColStride + 4 * p_h;
+                *reinterpret_cast<float4*>(q_pg) = make_float4(sp[0], sp[1], sp[2], sp[3]);
             }
         }
         if (WITH_LOSS) {
-            const int tt = tid >> 3, col = tid & 7, t = t0 + tt;
-            if (t < T)
-                reinterpret_cast<float4*>(a.dlogits)[(size_t)t * B + b0 + col] = out->dl[tt * kTraj + (col ^ (tt & 7))];
+            if (t0 + ltt < T) *q_dl = out->dl[lslot];
+            q_dl -= step;
+            q_dv -= step;
         }
+        q_vs -= step;
+        if (q_pg) q_pg -= step;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
