@@ -12,9 +12,10 @@
 // gradients in registers, and the results go back through shared memory so the global
 // stores are row-contiguous as well.
 //
-// Transcendentals use the hardware approximations (ex2/lg2.approx, relative error ~2^-22): the
-// arguments are differences from the row maximum (<= 0) and sums in [1, A], so the absolute
-// error stays ~1e-7, far inside the 1e-5 parity budget, at a third of the instruction count.
+// Transcendentals use the hardware approximations (ex2/lg2.approx.ftz, relative error ~2^-22) in
+// the base-2 domain: the arguments are differences from the row maximum (<= 0) and sums in
+// [1, A], so the absolute error stays ~1e-7, far inside the 1e-5 parity budget, at a fraction of
+// the instruction count of expf/logf.
 //
 // Reference quirks reproduced in IMPALA_MODE_REFERENCE:
 //   delta_t = rho_t (r_t + gamma v_{t+1} - v_0)                  learner.py:126  (v[:1])
@@ -28,6 +29,20 @@
 #include "common.cuh"
 
 namespace {
+
+// ex2 / lg2 hardware approximations with flush-to-zero (no denormal fix-up code): relative error
+// ~2^-22.  Softmax is evaluated in the base-2 domain: zs = z * log2(e), p_k = 2^(zs_k - lse2).
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 constexpr int kTraj = 8;             // trajectories (= warps) per CTA
 constexpr int kThreads = kTraj * 32;
@@ -185,6 +200,8 @@ __global__ void __launch_bounds__(kThreads, 3) vtrace_kernel(VtArgs a) {
                     zb[k] = s_beh[tt * LS + w * AP + k];
                 }
                 // log-softmax of both logit vectors (learner.py:298-303)
+#pragma unroll
+                for (int k = 0; k < AP; ++k) z[k] *= kLog2e, zb[k] *= kLog2e;  // base-2 domain
                 float mx = z[0], mxb = zb[0];
 #pragma unroll
                 for (int k = 1; k < AP; ++k)
@@ -192,14 +209,15 @@ __global__ void __launch_bounds__(kThreads, 3) vtrace_kernel(VtArgs a) {
                 float se = 0.f, seb = 0.f;
 #pragma unroll
                 for (int k = 0; k < AP; ++k)
-                    if (k < A) se += __expf(z[k] - mx), seb += __expf(zb[k] - mxb);
-                const float lse = mx + __logf(se), lseb = mxb + __logf(seb);
+                    if (k < A) se += ex2f(z[k] - mx), seb += ex2f(zb[k] - mxb);
+                const float lse = mx + lg2f(se), lseb = mxb + lg2f(seb);
                 float z_a = z[0], zb_a = zb[0];
 #pragma unroll
                 for (int k = 1; k < AP; ++k)
                     if (k == act) z_a = z[k], zb_a = zb[k];
-                const float lp_cur = z_a - lse, lp_beh = zb_a - lseb;
-                const float ratio = __expf(lp_cur - lp_beh);                   // :121-123
+                const float lp2_cur = z_a - lse, lp2_beh = zb_a - lseb;  // log2 pi(a)
+                const float lp_cur = lp2_cur * kLn2;
+                const float ratio = ex2f(lp2_cur - lp2_beh);                   // :121-123
                 const float rho = valid ? fminf(ratio, a.rho_bar) : 0.f;       // :124
                 const float cc = valid ? fminf(ratio, a.c_bar) : 0.f;          // :125
                 const float disc = (valid && !dn) ? a.gamma : 0.f;             // :109
@@ -237,8 +255,8 @@ __global__ void __launch_bounds__(kThreads, 3) vtrace_kernel(VtArgs a) {
                     float lz[AP], pk[AP];
 #pragma unroll
                     for (int k = 0; k < AP; ++k) {
-                        lz[k] = z[k] - lse;
-                        pk[k] = (k < A) ? __expf(lz[k]) : 0.f;
+                        lz[k] = (z[k] - lse) * kLn2;
+                        pk[k] = (k < A) ? ex2f(z[k] - lse) : 0.f;
                         if (k < A) ent -= pk[k] * lz[k];                       // :310-314, :153
                     }
 #pragma unroll
@@ -507,16 +525,19 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
             const float v_n = st.v[crow9 + kColStride];
             const int slot = cslot;
             const float4 zc = st.cur[slot], zbv = st.beh[slot];
-            const float z[4] = {zc.x, zc.y, zc.z, zc.w}, zb[4] = {zbv.x, zbv.y, zbv.z, zbv.w};
+            // base-2 domain: zs = z log2(e); log-softmax_k = (zs_k - lse2) ln 2   (learner.py:298-303)
+            const float z[4] = {zc.x * kLog2e, zc.y * kLog2e, zc.z * kLog2e, zc.w * kLog2e};
+            const float zb[4] = {zbv.x * kLog2e, zbv.y * kLog2e, zbv.z * kLog2e, zbv.w * kLog2e};
             const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
             const float mxb = fmaxf(fmaxf(zb[0], zb[1]), fmaxf(zb[2], zb[3]));
-            const float se = (__expf(z[0] - mx) + __expf(z[1] - mx)) + (__expf(z[2] - mx) + __expf(z[3] - mx));
-            const float seb = (__expf(zb[0] - mxb) + __expf(zb[1] - mxb)) + (__expf(zb[2] - mxb) + __expf(zb[3] - mxb));
-            const float lse = mx + __logf(se), lseb = mxb + __logf(seb);
+            const float se = (ex2f(z[0] - mx) + ex2f(z[1] - mx)) + (ex2f(z[2] - mx) + ex2f(z[3] - mx));
+            const float seb = (ex2f(zb[0] - mxb) + ex2f(zb[1] - mxb)) + (ex2f(zb[2] - mxb) + ex2f(zb[3] - mxb));
+            const float lse = mx + lg2f(se), lseb = mxb + lg2f(seb);
             const float z_a = act == 1 ? z[1] : (act == 2 ? z[2] : (act == 3 ? z[3] : z[0]));
             const float zb_a = act == 1 ? zb[1] : (act == 2 ? zb[2] : (act == 3 ? zb[3] : zb[0]));
-            const float lp_cur = z_a - lse, lp_beh = zb_a - lseb;
-            const float ratio = __expf(lp_cur - lp_beh);                   // :121-123
+            const float lp2_cur = z_a - lse, lp2_beh = zb_a - lseb;      // log2 pi(a)
+            const float lp_cur = lp2_cur * kLn2;
+            const float ratio = ex2f(lp2_cur - lp2_beh);                   // :121-123
             const float rho = valid ? fminf(ratio, a.rho_bar) : 0.f;       // :124
             const float cc = valid ? fminf(ratio, a.c_bar) : 0.f;          // :125
             const float disc = (valid && !dn) ? a.gamma : 0.f;             // :109
@@ -551,8 +572,8 @@ __global__ void __launch_bounds__(kThreads, 4) vtrace_fast_kernel(VtArgs a) {
                 float lz[4], pk[4], ent = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    lz[k] = z[k] - lse;
-                    pk[k] = __expf(lz[k]);
+                    pk[k] = ex2f(z[k] - lse);
+                    lz[k] = (z[k] - lse) * kLn2;
                     ent -= pk[k] * lz[k];                                  // :310-314, :153
                 }
                 float dz[4];
