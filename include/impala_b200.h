@@ -113,9 +113,10 @@ int impala_vtrace_loss(const float* cur_logits, const float* beh_logits, const i
  *   group 0 = [0, n_policy) (policy net), group 1 = [n_policy, n_total) (value net);
  *   each group is scaled by min(1, max_norm / (||g||_2 + 1e-6)) as
  *   torch.nn.utils.clip_grad_norm_ does, then one Adam step (no weight decay) with
- *   bias correction from the device-side counter *step (incremented by the kernel).
+ *   bias correction from the device-side optimizer state (updated by the kernel):
+ *   state = int64[3] {step count, beta1^step, beta2^step as float64 bits}; all zero = fresh.
  *   norms_out (f64[2], may be NULL) receives the two pre-clip norms. */
-int impala_clip_adam(float* params, const double* grad, float* m, float* v, int64_t* step,
+int impala_clip_adam(float* params, const double* grad, float* m, float* v, int64_t* state,
                      int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
                      float beta2, float eps, double* norms_out, void* stream);
 

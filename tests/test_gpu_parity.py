@@ -180,7 +180,7 @@ def test_clip_adam(ops, n_pi, n_vf, max_norm):
     params = dev(p0)
     m = torch.zeros(n, device="cuda")
     v = torch.zeros(n, device="cuda")
-    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    step = torch.zeros(3, dtype=torch.int64, device="cuda")  # step, beta1^t, beta2^t
     hp = default_hparams(max_norm=max_norm, lr=1e-3)
     ref_p = [p0[:n_pi].astype(np.float64), p0[n_pi:].astype(np.float64)]
     adam = orc.Adam(ref_p, hp.lr)
@@ -193,8 +193,8 @@ def test_clip_adam(ops, n_pi, n_vf, max_norm):
         nn = norms.cpu().numpy()
         assert abs(nn[0] - n0) < 1e-9 * max(1, n0) and abs(nn[1] - n1) < 1e-9 * max(1, n1)
         got = params.cpu().numpy()
-        assert np.abs(got - np.concatenate(ref_p)).max() < 2e-6
-    assert int(step.item()) == 3
+        assert np.abs(got - np.concatenate(ref_p)).max() < 3e-6
+    assert int(step[0].item()) == 3
 
 
 def _engine_for(g, use_graph):

@@ -74,7 +74,7 @@ class LearnerEngine:
         self.params = torch.zeros(self.n_total, **f32)
         self.adam_m = torch.zeros(self.n_total, **f32)
         self.adam_v = torch.zeros(self.n_total, **f32)
-        self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.adam_step = torch.zeros(3, dtype=torch.int64, device=self.dev)  # step, beta1^t, beta2^t bits
         # float64 [gradient | 4 loss scalars | pad]: the all-reduce payload
         self.comm = torch.zeros(self.n_total + 8, dtype=torch.float64, device=self.dev)
         self.norms = torch.zeros(2, dtype=torch.float64, device=self.dev)
