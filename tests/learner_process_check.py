@@ -34,7 +34,13 @@ def main():
     policy.load_state_dict({k: torch.from_numpy(init["policy"][k]).double() for k in PKEYS})
     value_fn.load_state_dict({k: torch.from_numpy(init["value_fn"][k]).double() for k in PKEYS})
     policy.share_memory()  # train.py:67
-    q = mp.Queue(maxsize=hp.queue_lim)
+    use_ring = len(sys.argv) > 2 and sys.argv[2] == "ring"
+    if use_ring:  # same actors, shared-memory slabs instead of pickled tensors
+        from torched_impala_b200.ring import RingQueue
+
+        q = RingQueue(c["T"], c["B"], c["O"], c["A"], slabs=2)
+    else:
+        q = mp.Queue(maxsize=hp.queue_lim)
     counter = Counter(0)
     log_dir = sys.argv[1] if len(sys.argv) > 1 else None
     lrn = Learner(1, hp, policy, value_fn, q, counter, log_path=log_dir, timeout=60)
@@ -63,7 +69,9 @@ def main():
         ck = os.path.join(log_dir, "l1", f"IMPALA_{hp.env_name}_l1_2.pt")
         assert os.path.exists(ck), ck
         assert set(torch.load(ck)) == {"policy_state_dict", "value_fn_state_dict"}
-    print(f"LEARNER_PROCESS_OK updates={counter.value} max|dW|={worst:.2e}")
+    if use_ring:
+        q.close()
+    print(f"LEARNER_PROCESS_OK updates={counter.value} max|dW|={worst:.2e} ring={use_ring}")
 
 
 if __name__ == "__main__":

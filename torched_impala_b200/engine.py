@@ -196,6 +196,22 @@ class LearnerEngine:
                     "impala_ingest")
         self.slab_ready[slot].record(cs)
 
+    def register_host(self, address: int, nbytes: int) -> None:
+        """Page-lock caller-owned host memory (e.g. a shared-memory trajectory ring) for DMA."""
+        rc = torch.cuda.cudart().cudaHostRegister(address, nbytes, 0)
+        if int(rc) != 0:
+            raise _cabi.ImpalaCudaError(f"cudaHostRegister failed: {rc}")
+
+    def ingest_from(self, host_address: int, slot: int = 0) -> None:
+        """Like `ingest`, but the source slab is caller-owned (registered) host memory in the
+        same batch layout - the DMA reads the actors' shared-memory slab directly."""
+        cs = self.copy_stream
+        if self._slab_used[slot]:
+            cs.wait_event(self.slab_free[slot])
+        _cabi.check(self.lib.impala_ingest(_ptr(self.d_slabs[slot]), C.c_void_p(host_address),
+                                           self.slab_bytes, C.c_void_p(cs.cuda_stream)), "impala_ingest")
+        self.slab_ready[slot].record(cs)
+
     def load_device_batch(self, batch: dict, slot: int = 0) -> None:
         """Convenience for kernel-only timing: put a batch in HBM and wait for it."""
         self.fill_host(batch, slot)

@@ -196,9 +196,25 @@ class Learner:
                 writer = SummaryWriter(self.log_path)
                 writer.add_text("hyperparameters", f"{self.hp}")
             done, slot = 0, 0
+            ring = self.q if hasattr(self.q, "collect_batch") else None  # ring.RingQueue
+            if ring is not None:
+                if ring.slab_bytes != eng.slab_bytes:
+                    raise ValueError("RingQueue and learner disagree on (T, B, obs, actions)")
+                eng.register_host(ring.slab_address(0), ring.slab_bytes * ring.K)
             while done < self.hp.max_updates:
-                reward = self._collect(eng.host_batch(slot), writer)
-                eng.ingest(slot)
+                if ring is None:
+                    reward = self._collect(eng.host_batch(slot), writer)
+                    eng.ingest(slot)
+                else:
+                    try:
+                        k, reward = ring.collect_batch(self.timeout)
+                    except queue.Empty:
+                        print(f"[learner_{self.id}] no trajectory for {self.timeout} s - giving up")
+                        self.completion.set()
+                        raise
+                    eng.ingest_from(ring.slab_address(k), slot)  # DMA straight out of shared memory
+                    eng.slab_ready[slot].synchronize()
+                    ring.release(k)
                 eng.step(slot)
                 sc = eng.read_scalars()
                 self._publish(eng)
