@@ -391,10 +391,13 @@ def run_own_arm(args):
     H, O, A = eng.H_pi, eng.O, eng.A
     on_tc = (os.environ.get("IMPALA_MLP_TC", "1") != "0" and O % 4 == 0 and 4 <= O <= 28
              and H in (128, 256) and A <= 4)
-    # tensor-core work actually issued: 3xTF32 (3 UMMAs per product), K padded to 32, and the
-    # backward runs two GEMMs per row (recompute + dW1 reduction)
-    executed = {"mlp_forward(policy)": 2.0 * eng.M_pi * H * 32 * 3, "mlp_forward(value_fn)": 2.0 * eng.M_vf * H * 32 * 3,
-                "mlp_backward(policy)": 2.0 * eng.M_pi * H * 32 * 6, "mlp_backward(value_fn)": 2.0 * eng.M_vf * H * 32 * 6}
+    # tensor-core work actually issued: 3xTF32 (3 UMMAs per product); forward K = [x | 1] padded to
+    # a multiple of 8; the backward runs two GEMMs per row: the recompute (K = O padded to 8, bias
+    # added on the CUDA cores) and the dW1 reduction (32 output columns)
+    kf, kb = (O + 1 + 7) // 8 * 8, (O + 7) // 8 * 8
+    executed = {"mlp_forward(policy)": 2.0 * eng.M_pi * H * kf * 3, "mlp_forward(value_fn)": 2.0 * eng.M_vf * H * kf * 3,
+                "mlp_backward(policy)": 2.0 * eng.M_pi * H * (kb + 32) * 3,
+                "mlp_backward(value_fn)": 2.0 * eng.M_vf * H * (kb + 32) * 3}
     kernels = {}
     for name, k in kern.items():
         ent = dict(us=round(k["us"], 3))

@@ -4,9 +4,12 @@
 // Transposed formulation so that a thread owns a HIDDEN unit (TMEM lane = hidden unit), per tile
 // of 64 batch rows:
 //
-//   UMMA1 (SS, recompute)  PRE[H, 64]  = W1'[H, K'] * X'[64, K']^T   X' = [x | 1 | 0], W1' = [W1 | b1 | 0]
-//   CUDA cores             h = relu(PRE);  dh = W2^T dz;  dW2 += dz h;  DP = (PRE > 0) ? dh : 0
-//   UMMA2 (TS, reduction)  dW1'[H, K'] += DP[H, 64] * X'[64, K']      column O of dW1' is db1
+//   UMMA1 (SS, recompute)  PRE[H, 64]  = W1'[H, K'] * X'[64, K']^T   X' = [x | 0], W1' = [W1 | 0]
+//   CUDA cores             pre = PRE + b1; h = relu(pre); dh = W2^T dz; dW2 += dz h;
+//                          DP = (pre > 0) ? dh : 0;  db1 += DP
+//   UMMA2 (TS, reduction)  dW1'[H, K'] += DP[H, 64] * X'[64, K']
+// (b1 / db1 stay on the CUDA cores: folding them into K would cost a fourth K step of UMMA1 at
+// O = 24, i.e. a third more accumulator columns streamed, for one FADD per element.)
 //
 // PRE lands in TMEM; the epilogue thread that owns lane j reads its 64 pre-activations, and
 // writes DP back INTO TENSOR MEMORY (hi in place of PRE, lo in a second region) with tcgen05.st,
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     TRACE(0, 15)
 
     // ---- one-time setup
-    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads);
+    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/false);
     tc::fence_proxy_async();
     if (warp == 10) {
         tc::tmem_alloc(&bars->tmem_base, 512);
@@ -131,6 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         float gb2 = 0.f;
         if (blk < nblk) {
             float w2r[NP], gw2[NP];
+            const float b1j = __ldg(b1 + j);
+            float gb1 = 0.f;
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
                 w2r[n] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                         } else {
                             dz[0] = dz_tile[32 * hh + r];
                         }
-                        const float pre = v[r], h = fmaxf(pre, 0.f);
+                        const float pre = v[r] + b1j, h = fmaxf(pre, 0.f);
                         float dh = 0.f;
 #pragma unroll
                         for (int n = 0; n < NP; ++n) {
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                             gw2[n] = fmaf(dz[n], h, gw2[n]);
                         }
                         const float dp = pre > 0.f ? dh : 0.f;  // relu'(0) = 0 as in torch
+                        gb1 += dp;
                         tc::split_tf32(dp, v[r], lo[hh][r]);
                     }
                     tc::tmem_st32(c_hi + 32 * hh, v);  // DP_hi replaces PRE in place
@@ -200,8 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 if (k < O) wsb[a.lay.oW1 + (size_t)j * O + k] = g[k];
-                else if (k == O) wsb[a.lay.ob1 + j] = g[k];
             }
+            wsb[a.lay.ob1 + j] = gb1;
 #pragma unroll
             for (int n = 0; n < NP; ++n)
                 if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = gw2[n];
@@ -266,9 +272,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
                         if (n < a.N2) z[n] = __ldg(a.dout + (size_t)row * a.N2 + n);
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1 / collects db1
             asm volatile("bar.sync 1, 64;" ::: "memory");  // both producer warps drained the raw stage
             if (i + kRawStages < n_my) issue_raw(i + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 64 batch rows
         const uint32_t idesc2w = tc::instr_desc_tf32_m128(2 * kKPad);  // N = 64: [hi | lo] features
         const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);       // N = 32: hi features
-        const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use (data + bias column)
+        const int ksteps1 = (O + 7) >> 3;  // K' columns in use
         const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
         const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
         const uint64_t dxt = tc::smem_desc_k_sw128(xt, 0);

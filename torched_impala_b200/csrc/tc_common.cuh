@@ -227,7 +227,7 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c16) {
 // trips).  nthreads <= 8 * 256 / MAXIT must hold for H <= 256: MAXIT = 8 covers >= 256 threads.
 __device__ __forceinline__ void stage_w1_tiles(uint8_t* w_hi, uint8_t* w_lo, const float* __restrict__ W1,
                                                const float* __restrict__ b1, int H, int O, int tid,
-                                               int nthreads) {
+                                               int nthreads, bool bias_column = true) {
     constexpr int MAXIT = 8;
     const int ochunks = O >> 2;
     float4 v[MAXIT];
@@ -238,7 +238,7 @@ __device__ __forceinline__ void stage_w1_tiles(uint8_t* w_hi, uint8_t* w_lo, con
         if (idx < H * 8) {
             const int j = idx >> 3, c = idx & 7;
             if (c < ochunks) v[it] = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)j * O) + c);
-            else if (c == ochunks) v[it].x = __ldg(b1 + j);
+            else if (c == ochunks && bias_column) v[it].x = __ldg(b1 + j);
         }
     }
 #pragma unroll
