@@ -67,7 +67,10 @@ int impala_ingest(void* dev_slab, const void* host_slab, int64_t bytes, void* st
 int impala_mlp_forward(const float* x, const float* params, float* out, int M, int O, int H,
                        int N2, void* stream);
 
-/* Bytes of scratch impala_mlp_backward needs for these dimensions. */
+/* Bytes of scratch impala_mlp_backward needs for these dimensions.  The caller zero-fills
+ * it ONCE after allocation; every call leaves its control words zeroed again (the tensor-core
+ * kernel meets at a self-re-arming grid barrier before its in-kernel reduction; on a workspace
+ * that was never zeroed it traps - a launch failure, not a hang). */
 int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2);
 
 /* Gradient of sum_m <dout[m,:], mlp(x[m,:])> w.r.t. the parameter block, written

@@ -35,6 +35,7 @@ std::map<std::tuple<const void*, int, int, size_t>, GridInfo> g_cfg_cache;
 // one fully coalesced line and 8 x 4 loads are in flight per entry.  Fixed summation
 // order -> bitwise reproducible gradients.
 constexpr int kRedWarps = 8;
+constexpr int64_t kWsHeader = 256;  // control words of the tensor-core backward's grid barrier
 __global__ void __launch_bounds__(kRedWarps * 32)
 reduce_partials_kernel(const float* __restrict__ ws, double* __restrict__ grad, int nparts,
                        int64_t total) {
@@ -166,7 +167,7 @@ extern "C" int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2) {
     if (M < 1 || !pick_config(O, H, N2, true, &c)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
     int64_t tiles = (M + kRows - 1) / kRows;
     if (tiles > kMaxParts) tiles = kMaxParts;
-    return tiles * impala_make_layout(O, H, N2).total * (int64_t)sizeof(float);
+    return kWsHeader + tiles * impala_make_layout(O, H, N2).total * (int64_t)sizeof(float);
 }
 
 extern "C" int impala_mlp_backward(const float* x, const float* params, const float* dout,
@@ -179,14 +180,16 @@ extern "C" int impala_mlp_backward(const float* x, const float* params, const fl
     if (!fill_args(&a, &c, &smem, true, M, O, H, N2)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
     if (workspace_bytes < impala_mlp_backward_workspace(M, O, H, N2))
         return IMPALA_ERR_WORKSPACE_TOO_SMALL;
-    a.x = x, a.params = params, a.dout = dout, a.ws = (float*)workspace;
+    // workspace = [control words (kWsHeader bytes, zero-filled once by the caller) | partial rows]
+    a.x = x, a.params = params, a.dout = dout;
+    a.ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + kWsHeader);
     int grid = 0;
-    int rc;
     const char* tc_env = std::getenv("IMPALA_MLP_TC");
-    if (!(tc_env && tc_env[0] == '0') && impala_mlp_bwd_tc_eligible(x, dout, M, O, H, N2))
-        rc = impala_mlp_bwd_tc(x, params, dout, a.ws, M, O, H, N2, (cudaStream_t)stream, &grid);
-    else
-        rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
+    if (!(tc_env && tc_env[0] == '0') && impala_mlp_bwd_tc_eligible(x, dout, M, O, H, N2) &&
+        (reinterpret_cast<uintptr_t>(grad) & 15) == 0)
+        return impala_mlp_bwd_tc(x, params, dout, a.ws, grad, static_cast<unsigned int*>(workspace), M, O, H,
+                                 N2, (cudaStream_t)stream);  // reduces in-kernel
+    const int rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
     if (rc != IMPALA_OK) return rc;
     const int64_t total = a.lay.total;
     reduce_partials_kernel<<<(unsigned)((total + 31) / 32), kRedWarps * 32, 0,

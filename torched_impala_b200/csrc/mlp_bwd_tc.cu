@@ -32,6 +32,12 @@
 //   warps 0-7   epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
 //   warps 8-9   producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo tiles
 //   warp  10    TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
+//
+// Cross-CTA reduction: every CTA writes its float32 partial gradient row, the grid meets at an
+// arrival counter (grid <= SM count and one CTA per SM, so all CTAs are co-resident), and CTA c
+// then sums entries [64c, 64c+64) over all rows in float64 in a fixed order - the rows are still
+// in L2, the result is bitwise reproducible, and no second launch sits between the two backward
+// kernels of a step.
 #include <cstdlib>
 
 #include "mlp_kernels.cuh"
@@ -61,6 +67,8 @@ struct BwdTcArgs {
     const float* params;
     const float* dout;
     float* ws;
+    double* grad;        // float64 [lay.total], written by the in-kernel reduction
+    unsigned int* ctl;   // {arrivals, departures}: zero on entry, zero on exit
     int M, O, H, N2, num_tiles;
     int trace;
     MlpLayout lay;
@@ -96,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
     const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     __shared__ long long s_trace[24 * 16];
+    __shared__ long long s_trace_t[2];
     const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 10);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
@@ -203,10 +212,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) g[k] += g2[k];
             float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
+            float4* wrow = reinterpret_cast<float4*>(wsb + a.lay.oW1 + (size_t)j * O);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k < O) wsb[a.lay.oW1 + (size_t)j * O + k] = g[k];
-            }
+            for (int c = 0; c < 8; ++c)
+                if (c < ochunks) wrow[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
             wsb[a.lay.ob1 + j] = gb1;
 #pragma unroll
             for (int n = 0; n < NP; ++n)
@@ -375,13 +384,67 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     }
 
     tc::tc_fence_before();
+    __threadfence();  // this thread's partial-row stores are visible device-wide
     __syncthreads();
     if (warp == 10) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+
+    // ---- grid barrier (all CTAs are resident), then a deterministic float64 reduction of the
+    // partial rows; a workspace that was not zero-filled once traps instead of hanging.
+    if (tid == 0) {
+        atomicAdd(a.ctl, 1u);
+        const long long t0 = clock64();
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.ctl) : "memory");
+            if (seen != gridDim.x && clock64() - t0 > (1ll << 32)) __trap();
+        } while (seen != gridDim.x);
+        s_trace_t[0] = clock64();
+    }
+    __syncthreads();
+    {
+        const int64_t total = a.lay.total;  // multiple of 32
+        const int nchunks = (int)((total + 63) >> 6), nparts = (int)gridDim.x;
+        double* s_red = reinterpret_cast<double*>(raw);  // [kThreads / 32][64]; the ring is idle now
+        for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const int64_t e0 = (int64_t)c * 64 + 2 * lane;
+            double sx = 0.0, sy = 0.0;
+            if (e0 < total) {
+                const float* col = a.ws + e0;
+                int p = warp;
+                for (; p + 3 * 11 < nparts; p += 4 * 11) {
+                    const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
+                    const float2 v1 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 11) * total));
+                    const float2 v2 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 22) * total));
+                    const float2 v3 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 33) * total));
+                    sx += v0.x, sy += v0.y, sx += v1.x, sy += v1.y;
+                    sx += v2.x, sy += v2.y, sx += v3.x, sy += v3.y;
+                }
+                for (; p < nparts; p += 11) {
+                    const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
+                    sx += v0.x, sy += v0.y;
+                }
+            }
+            s_red[warp * 64 + 2 * lane] = sx;
+            s_red[warp * 64 + 2 * lane + 1] = sy;
+            __syncthreads();
+            if (warp == 0 && e0 < total) {
+                double tx = 0.0, ty = 0.0;
+#pragma unroll
+                for (int w = 0; w < 11; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
+                *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && atomicAdd(a.ctl + 1, 1u) == gridDim.x - 1) {  // last CTA out re-arms the barrier
+        a.ctl[0] = 0u;
+        a.ctl[1] = 0u;
+    }
     if (a.trace && blockIdx.x == 0) {
-        if (tid == 0) s_trace[1 * 16 + 15] = clock64();
+        if (tid == 0) s_trace[1 * 16 + 15] = clock64(), s_trace[2 * 16 + 15] = s_trace_t[0];
         __syncthreads();
         for (int k = tid; k < 24 * 16; k += kThreads) g_trace[k] = s_trace[k];
     }
@@ -400,12 +463,12 @@ bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O,
            (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
 }
 
-// Writes per-CTA partial gradient rows into ws (same layout as the FP32 kernel) and returns the
-// number of rows in *grid_out; the caller reduces them.
-int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws, int M,
-                      int O, int H, int N2, cudaStream_t st, int* grid_out) {
+// Per-CTA partial gradient rows go to ws (same layout as the FP32 kernel), their float64 sum to
+// grad; ctl = two zeroed control words (see the grid barrier in the kernel).
+int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
+                      double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st) {
     BwdTcArgs a{};
-    a.x = x, a.params = params, a.dout = dout, a.ws = ws;
+    a.x = x, a.params = params, a.dout = dout, a.ws = ws, a.grad = grad, a.ctl = ctl;
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
     a.num_tiles = (M + kRowsT - 1) / kRowsT;
     a.lay = impala_make_layout(O, H, N2);
@@ -430,7 +493,6 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     int grid = a.num_tiles < sms ? a.num_tiles : sms;
     if (grid > kMaxParts) grid = kMaxParts;
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
-    *grid_out = grid;
     return impala_launch_status();
 }
 

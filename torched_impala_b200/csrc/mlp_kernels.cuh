@@ -36,8 +36,8 @@ int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, in
 
 // Tensor-core backward (mlp_bwd_tc.cu): per-CTA partial rows into ws, *grid_out rows written.
 bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O, int H, int N2);
-int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws, int M,
-                      int O, int H, int N2, cudaStream_t st, int* grid_out);
+int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
+                      double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st);
 
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \

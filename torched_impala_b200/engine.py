@@ -125,6 +125,7 @@ class LearnerEngine:
 
         self._graph_main = [None] * slabs
         self._graph_opt = None
+        self._main_launches = 0
         self.steps_done = 0
 
     # ------------------------------------------------------------------ parameters
@@ -247,7 +248,16 @@ class LearnerEngine:
         _cabi.check(lib.impala_mlp_backward(obs, p_vf, _ptr(self.dv), g_vf, _ptr(self.ws_vf),
                                             self.ws_vf_bytes, self.M_vf, O, self.H_v, 1, st),
                     "impala_mlp_backward(value_fn)")
-        return 7  # 2 fwd + 1 vtrace_loss + 2 x (bwd + partial reduce)
+        return 3 + self._bwd_launches(self.H_pi, A) + self._bwd_launches(self.H_v, 1)
+
+    def _bwd_launches(self, H: int, N2: int) -> int:
+        """Kernels behind one impala_mlp_backward call: the tensor-core kernel reduces its per-CTA
+        partial rows itself, the FP32 kernel is followed by a reduction launch (csrc/mlp.cu)."""
+        import os
+
+        tc = (os.environ.get("IMPALA_MLP_TC", "1")[:1] != "0" and self.O % 4 == 0 and 4 <= self.O <= 28
+              and H in (128, 256) and N2 <= 4)
+        return 1 if tc else 2
 
     def _enqueue_opt(self) -> int:
         hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -262,9 +272,11 @@ class LearnerEngine:
         with torch.cuda.stream(self.stream):
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, stream=self.stream):
-                self._enqueue_main(slot)
+                self._main_launches = self._enqueue_main(slot)
+                if self.world == 1:  # no collective in between: the optimizer joins the same graph
+                    self._enqueue_opt()
             self._graph_main[slot] = g1
-            if self._graph_opt is None:
+            if self.world > 1 and self._graph_opt is None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, stream=self.stream):
                     self._enqueue_opt()
@@ -278,16 +290,20 @@ class LearnerEngine:
                 if self._graph_main[slot] is None:
                     self._capture(slot)
                 self._graph_main[slot].replay()
-                n = 7
+                n = self._main_launches
+                fused_opt = self.world == 1
             else:
                 n = self._enqueue_main(slot)  # first step eager: fills the launch-config caches
+                fused_opt = False
             self.slab_free[slot].record(self.stream)
             self._slab_used[slot] = True
             if self.world > 1:
                 import torch.distributed as dist
 
                 dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)
-            if self.use_graph and self._graph_opt is not None:
+            if fused_opt:
+                n += 1
+            elif self.use_graph and self._graph_opt is not None:
                 self._graph_opt.replay()
                 n += 1
             else:

@@ -69,7 +69,7 @@ def mlp_backward(x, params, dout, O: int, H: int, N2: int):
     nbytes = lib.impala_mlp_backward_workspace(M, O, H, N2)
     if nbytes < 0:
         _cabi.check(int(nbytes), "impala_mlp_backward_workspace")
-    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+    ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=x.device)  # control words start at 0
     grad = torch.empty(total, dtype=torch.float64, device=x.device)
     _cabi.check(lib.impala_mlp_backward(_p(x), _p(params), _p(dout), _p(grad), _p(ws), int(nbytes),
                                         M, O, H, N2, _st()), "impala_mlp_backward")
