@@ -67,6 +67,15 @@ int impala_ingest(void* dev_slab, const void* host_slab, int64_t bytes, void* st
 int impala_mlp_forward(const float* x, const float* params, float* out, int M, int O, int H,
                        int N2, void* stream);
 
+/* Both networks of one learner step in one launch: logits = policy(x[0..M_pi)), values =
+ * value_fn(x[0..M_vf)) on the SAME observation rows (learner.py:112-113: `self.policy(obs[:-1])`
+ * and `self.value_fn(obs)`; M_pi = T*B, M_vf = (T+1)*B).  Results are identical to two
+ * impala_mlp_forward calls; where the tensor-core path covers both shapes the SMs are split
+ * between the two tile lists so the step pays one prologue and one launch. */
+int impala_mlp_forward_pair(const float* x, const float* params_pi, const float* params_vf,
+                            float* logits, float* values, int M_pi, int M_vf, int O, int H_pi,
+                            int H_vf, int A, void* stream);
+
 /* Bytes of scratch impala_mlp_backward needs for these dimensions.  The caller zero-fills
  * it ONCE after allocation; every call leaves its control words zeroed again (the tensor-core
  * kernel meets at a self-re-arming grid barrier before its in-kernel reduction; on a workspace
@@ -80,6 +89,16 @@ int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2);
 int impala_mlp_backward(const float* x, const float* params, const float* dout, double* grad,
                         void* workspace, int64_t workspace_bytes, int M, int O, int H, int N2,
                         void* stream);
+
+/* The MLP part of the single loss.backward() at learner.py:175 for both networks in one launch:
+ * same results as impala_mlp_backward(policy; dout = dlogits) followed by
+ * impala_mlp_backward(value_fn; dout = dv), each with its own workspace (sized by
+ * impala_mlp_backward_workspace, zero-filled once). */
+int impala_mlp_backward_pair(const float* x, const float* params_pi, const float* params_vf,
+                             const float* dlogits, const float* dv, double* grad_pi, double* grad_vf,
+                             void* workspace_pi, int64_t workspace_pi_bytes, void* workspace_vf,
+                             int64_t workspace_vf_bytes, int M_pi, int M_vf, int O, int H_pi,
+                             int H_vf, int A, void* stream);
 
 /* V-trace only (learner.py:116-135): from current/behaviour logits, actions,
  * rewards, done, lens and the value estimates v (T+1,B) produce

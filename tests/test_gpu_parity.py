@@ -90,6 +90,37 @@ def test_mlp_backward(ops, monkeypatch, M, O, H, N2, tensor_cores):
     assert abs(total - real) <= 1e-12 * max(1.0, real)
 
 
+PAIR_SHAPES = [
+    # (T, B, O, H_pi, H_vf, A): M_pi = T*B, M_vf = (T+1)*B
+    (20, 64, 24, 256, 256, 4), (20, 1024, 24, 256, 256, 4), (5, 7, 8, 128, 256, 2), (3, 50, 28, 256, 128, 3),
+    (20, 4096, 24, 256, 256, 4), (20, 8, 4, 32, 32, 2), (9, 33, 64, 512, 512, 4),
+]
+
+
+@pytest.mark.parametrize("T,B,O,H_pi,H_vf,A", PAIR_SHAPES)
+def test_mlp_pair_matches_single_calls(ops, T, B, O, H_pi, H_vf, A):
+    """impala_mlp_forward_pair / impala_mlp_backward_pair (both networks in one launch where the
+    tensor-core path covers them, two launches otherwise) against the per-network entry points:
+    the forward bit for bit, the backward to float64 rounding (only the number of float32 partial
+    rows that are summed differs) - and so transitively against the oracle."""
+    rng = np.random.default_rng(T * B + O)
+    M_pi, M_vf = T * B, (T + 1) * B
+    pp = ops.pack_params(synth.init_params(1, O, A, H_pi)["policy"])
+    pv = ops.pack_params(synth.init_params(2, O, 1, H_vf)["policy"])
+    x = dev(rng.standard_normal((M_vf, O), dtype=np.float32))
+    dlog = dev((rng.standard_normal((M_pi, A), dtype=np.float32) / M_pi).astype(np.float32))
+    dv = dev((rng.standard_normal((M_vf,), dtype=np.float32) / M_vf).astype(np.float32))
+    logits, values = ops.mlp_forward_pair(x, pp, pv, M_pi, M_vf, O, H_pi, H_vf, A)
+    assert torch.equal(logits, ops.mlp_forward(x[:M_pi], pp, O, H_pi, A))
+    assert torch.equal(values, ops.mlp_forward(x, pv, O, H_vf, 1).reshape(-1))
+    for rep in range(2):  # twice: the grid barrier re-arms itself
+        g_pi, g_vf = ops.mlp_backward_pair(x, pp, pv, dlog, dv, O, H_pi, H_vf, A)
+        for got, want in ((g_pi, ops.mlp_backward(x[:M_pi], pp, dlog, O, H_pi, A)),
+                          (g_vf, ops.mlp_backward(x, pv, dv.reshape(-1, 1), O, H_vf, 1))):
+            scale = float(want.abs().max())
+            assert float((got - want).abs().max()) <= 5e-6 * scale + 1e-12, rep
+
+
 def _oracle_forward(g, u):
     lrn = orc.BatchedLearner(g.init_params() if u == 0 else g.params_after(u - 1), g.hp)
     return lrn.forward_backward(g.batch(u))

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/impala_b200.h"
 
@@ -28,6 +29,42 @@ static inline MlpLayout impala_make_layout(int O, int H, int N2) {
 static inline int impala_launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
+// SM count of the current device (cached per device).
+static inline cudaError_t impala_sm_count(int* out) {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !cached[dev]) {
+        int n = 0;
+        if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return *out = n, cudaSuccess;
+        cached[dev] = n;
+    }
+    *out = cached[dev];
+    return cudaSuccess;
+}
+
+static inline int impala_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// A persistent launch of `grid` CTAs shared by two tile lists (policy / value network): how many
+// CTAs take list A so that the slower side finishes earliest, for per-tile cost weights wa, wb.
+static inline int impala_pair_split(int tiles_a, int tiles_b, int grid, int64_t wa, int64_t wb) {
+    int best = 1;
+    int64_t best_cost = INT64_MAX, best_sum = INT64_MAX;
+    for (int na = 1; na < grid; ++na) {
+        const int nb = grid - na;
+        if (na > tiles_a || nb > tiles_b) continue;
+        const int64_t ca = (int64_t)((tiles_a + na - 1) / na) * wa, cb = (int64_t)((tiles_b + nb - 1) / nb) * wb;
+        const int64_t cost = ca > cb ? ca : cb, sum = ca + cb;
+        if (cost < best_cost || (cost == best_cost && sum < best_sum)) best = na, best_cost = cost, best_sum = sum;
+    }
+    return best;
 }
 
 __device__ __forceinline__ double warp_sum_f64(double x) {

@@ -162,6 +162,25 @@ extern "C" int impala_mlp_forward(const float* x, const float* params, float* ou
     return dispatch(false, a, c, smem, (cudaStream_t)stream, &grid);
 }
 
+static bool pair_enabled() {
+    const char* tc_env = std::getenv("IMPALA_MLP_TC");
+    const char* pr_env = std::getenv("IMPALA_MLP_PAIR");
+    return !(tc_env && tc_env[0] == '0') && !(pr_env && pr_env[0] == '0');
+}
+
+extern "C" int impala_mlp_forward_pair(const float* x, const float* params_pi, const float* params_vf,
+                                       float* logits, float* values, int M_pi, int M_vf, int O,
+                                       int H_pi, int H_vf, int A, void* stream) {
+    if (!x || !params_pi || !params_vf || !logits || !values) return IMPALA_ERR_BAD_ARG;
+    if (pair_enabled() && A >= 2 && A <= 4 && impala_mlp_fwd_tc_eligible(x, M_pi, O, H_pi, A) &&
+        impala_mlp_fwd_tc_eligible(x, M_vf, O, H_vf, 1))
+        return impala_mlp_fwd_tc_pair(x, params_pi, params_vf, logits, values, M_pi, M_vf, O, H_pi, H_vf, A,
+                                      (cudaStream_t)stream);
+    const int rc = impala_mlp_forward(x, params_pi, logits, M_pi, O, H_pi, A, stream);
+    if (rc != IMPALA_OK) return rc;
+    return impala_mlp_forward(x, params_vf, values, M_vf, O, H_vf, 1, stream);
+}
+
 extern "C" int64_t impala_mlp_backward_workspace(int M, int O, int H, int N2) {
     MlpConfig c{};
     if (M < 1 || !pick_config(O, H, N2, true, &c)) return IMPALA_ERR_UNSUPPORTED_SHAPE;
@@ -195,4 +214,32 @@ extern "C" int impala_mlp_backward(const float* x, const float* params, const fl
     reduce_partials_kernel<<<(unsigned)((total + 31) / 32), kRedWarps * 32, 0,
                              (cudaStream_t)stream>>>(a.ws, grad, grid, total);
     return impala_launch_status();
+}
+
+extern "C" int impala_mlp_backward_pair(const float* x, const float* params_pi, const float* params_vf,
+                                        const float* dlogits, const float* dv, double* grad_pi,
+                                        double* grad_vf, void* workspace_pi, int64_t workspace_pi_bytes,
+                                        void* workspace_vf, int64_t workspace_vf_bytes, int M_pi, int M_vf,
+                                        int O, int H_pi, int H_vf, int A, void* stream) {
+    if (!x || !params_pi || !params_vf || !dlogits || !dv || !grad_pi || !grad_vf || !workspace_pi ||
+        !workspace_vf)
+        return IMPALA_ERR_BAD_ARG;
+    if (pair_enabled() && A >= 2 && A <= 4 && impala_mlp_bwd_tc_eligible(x, dlogits, M_pi, O, H_pi, A) &&
+        impala_mlp_bwd_tc_eligible(x, dv, M_vf, O, H_vf, 1) &&
+        ((reinterpret_cast<uintptr_t>(grad_pi) | reinterpret_cast<uintptr_t>(grad_vf)) & 15) == 0) {
+        const int64_t need_pi = impala_mlp_backward_workspace(M_pi, O, H_pi, A);
+        const int64_t need_vf = impala_mlp_backward_workspace(M_vf, O, H_vf, 1);
+        if (need_pi < 0 || need_vf < 0) return IMPALA_ERR_UNSUPPORTED_SHAPE;
+        if (workspace_pi_bytes < need_pi || workspace_vf_bytes < need_vf) return IMPALA_ERR_WORKSPACE_TOO_SMALL;
+        return impala_mlp_bwd_tc_pair(
+            x, params_pi, params_vf, dlogits, dv,
+            reinterpret_cast<float*>(static_cast<char*>(workspace_pi) + kWsHeader),
+            reinterpret_cast<float*>(static_cast<char*>(workspace_vf) + kWsHeader), grad_pi, grad_vf,
+            static_cast<unsigned int*>(workspace_pi), M_pi, M_vf, O, H_pi, H_vf, A, (cudaStream_t)stream);
+    }
+    const int rc = impala_mlp_backward(x, params_pi, dlogits, grad_pi, workspace_pi, workspace_pi_bytes, M_pi,
+                                       O, H_pi, A, stream);
+    if (rc != IMPALA_OK) return rc;
+    return impala_mlp_backward(x, params_vf, dv, grad_vf, workspace_vf, workspace_vf_bytes, M_vf, O, H_vf, 1,
+                               stream);
 }

@@ -80,8 +80,12 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
 };
 
+// One persistent CTA's share of a network's backward: CTA `cta` of `ncta` takes tiles cta,
+// cta + ncta, ... and leaves its float32 partial gradient in row `cta` of a.ws.  Returns the
+// (idle) bulk-copy ring for use as scratch by the reduction.
 template <int NP>
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
+__device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int cta, const int ncta,
+                                                long long* s_trace) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by OFFSETTING the __shared__ array (a round trip through an integer
     // would make every derived pointer generic: LD/ST instead of LDS/STS)
@@ -102,9 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
     const float* __restrict__ b1 = a.params + a.lay.ob1;
     const float* __restrict__ W2 = a.params + a.lay.oW2;
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
-    const int n_my = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    __shared__ long long s_trace[24 * 16];
-    __shared__ long long s_trace_t[2];
+    const int n_my = (a.num_tiles - cta + ncta - 1) / ncta;
     const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 10);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
             tc::tmem_ld32(lane_addr + kColAcc + blk * 64 + 32, g2);  // dp_hi*x_lo
 #pragma unroll
             for (int k = 0; k < 32; ++k) g[k] += g2[k];
-            float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
+            float* wsb = a.ws + (size_t)cta * a.lay.total;
             float4* wrow = reinterpret_cast<float4*>(wsb + a.lay.oW1 + (size_t)j * O);
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         }
         // pads of the partial row (all 256 epilogue threads)
         {
-            float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
+            float* wsb = a.ws + (size_t)cta * a.lay.total;
             const int64_t lo4[4] = {a.lay.oW1 + (int64_t)H * O, a.lay.ob1 + H,
                                     a.lay.oW2 + (int64_t)a.N2 * H, a.lay.ob2 + a.N2};
             const int64_t hi4[4] = {a.lay.ob1, a.lay.oW2, a.lay.ob2, a.lay.total};
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         // ===================== producer (2 warps, 32 rows of the tile each) =====================
         const int pw = warp - 8, r = 32 * pw + lane;  // row of the tile this thread converts
         const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
-        auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+        auto tile_of = [&](int i) { return cta + i * ncta; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kRowsT <= a.M; };
         auto issue_raw = [&](int i) {
             if (pw == 0 && lane == 0 && is_full(i)) {
@@ -390,65 +392,109 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(BwdTcArgs a) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+#undef TRACE
+    return raw;
+}
 
-    // ---- grid barrier (all CTAs are resident), then a deterministic float64 reduction of the
-    // partial rows; a workspace that was not zero-filled once traps instead of hanging.
-    if (tid == 0) {
-        atomicAdd(a.ctl, 1u);
+// Grid barrier: every CTA of the launch is resident (grid <= SM count, one CTA per SM).  ctl[0]
+// counts arrivals; a workspace that was not zero-filled once traps instead of hanging.
+__device__ __forceinline__ void grid_arrive_and_wait(unsigned int* ctl) {
+    if (threadIdx.x == 0) {
+        atomicAdd(ctl, 1u);
         const long long t0 = clock64();
         unsigned int seen;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.ctl) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctl) : "memory");
             if (seen != gridDim.x && clock64() - t0 > (1ll << 32)) __trap();
         } while (seen != gridDim.x);
-        s_trace_t[0] = clock64();
     }
     __syncthreads();
-    {
-        const int64_t total = a.lay.total;  // multiple of 32
-        const int nchunks = (int)((total + 63) >> 6), nparts = (int)gridDim.x;
-        double* s_red = reinterpret_cast<double*>(raw);  // [kThreads / 32][64]; the ring is idle now
-        for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-            const int64_t e0 = (int64_t)c * 64 + 2 * lane;
-            double sx = 0.0, sy = 0.0;
-            if (e0 < total) {
-                const float* col = a.ws + e0;
-                int p = warp;
-                for (; p + 3 * 11 < nparts; p += 4 * 11) {
-                    const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
-                    const float2 v1 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 11) * total));
-                    const float2 v2 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 22) * total));
-                    const float2 v3 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 33) * total));
-                    sx += v0.x, sy += v0.y, sx += v1.x, sy += v1.y;
-                    sx += v2.x, sy += v2.y, sx += v3.x, sy += v3.y;
-                }
-                for (; p < nparts; p += 11) {
-                    const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
-                    sx += v0.x, sy += v0.y;
-                }
+}
+
+// The last CTA out re-arms the barrier for the next launch.
+__device__ __forceinline__ void grid_depart(unsigned int* ctl) {
+    if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+        ctl[0] = 0u;
+        ctl[1] = 0u;
+    }
+}
+
+// Deterministic float64 sum of `nparts` partial rows: chunk c = entries [64c, 64c + 64); this CTA
+// takes chunks first, first + stride, ...; warp w adds rows w, w + 11, ... and warp 0 combines.
+__device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts, const int first,
+                                            const int stride, double* s_red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = a.lay.total;  // multiple of 32
+    const int nchunks = (int)((total + 63) >> 6);
+    for (int c = first; c < nchunks; c += stride) {
+        const int64_t e0 = (int64_t)c * 64 + 2 * lane;
+        double sx = 0.0, sy = 0.0;
+        if (e0 < total) {
+            const float* col = a.ws + e0;
+            int p = warp;
+            for (; p + 3 * 11 < nparts; p += 4 * 11) {
+                const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
+                const float2 v1 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 11) * total));
+                const float2 v2 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 22) * total));
+                const float2 v3 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 33) * total));
+                sx += v0.x, sy += v0.y, sx += v1.x, sy += v1.y;
+                sx += v2.x, sy += v2.y, sx += v3.x, sy += v3.y;
             }
-            s_red[warp * 64 + 2 * lane] = sx;
-            s_red[warp * 64 + 2 * lane + 1] = sy;
-            __syncthreads();
-            if (warp == 0 && e0 < total) {
-                double tx = 0.0, ty = 0.0;
-#pragma unroll
-                for (int w = 0; w < 11; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
-                *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
+            for (; p < nparts; p += 11) {
+                const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
+                sx += v0.x, sy += v0.y;
             }
-            __syncthreads();
         }
-    }
-    if (tid == 0 && atomicAdd(a.ctl + 1, 1u) == gridDim.x - 1) {  // last CTA out re-arms the barrier
-        a.ctl[0] = 0u;
-        a.ctl[1] = 0u;
-    }
-    if (a.trace && blockIdx.x == 0) {
-        if (tid == 0) s_trace[1 * 16 + 15] = clock64(), s_trace[2 * 16 + 15] = s_trace_t[0];
+        s_red[warp * 64 + 2 * lane] = sx;
+        s_red[warp * 64 + 2 * lane + 1] = sy;
         __syncthreads();
-        for (int k = tid; k < 24 * 16; k += kThreads) g_trace[k] = s_trace[k];
+        if (warp == 0 && e0 < total) {
+            double tx = 0.0, ty = 0.0;
+#pragma unroll
+            for (int w = 0; w < 11; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
+            *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
+        }
+        __syncthreads();
     }
-#undef TRACE
+}
+
+__device__ __forceinline__ void dump_trace(const BwdTcArgs& a, long long* s_trace, long long t_barrier) {
+    if (a.trace && blockIdx.x == 0) {
+        if (threadIdx.x == 0) s_trace[1 * 16 + 15] = clock64(), s_trace[2 * 16 + 15] = t_barrier;
+        __syncthreads();
+        for (int k = threadIdx.x; k < 24 * 16; k += kThreads) g_trace[k] = s_trace[k];
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(const __grid_constant__ BwdTcArgs a) {
+    __shared__ long long s_trace[24 * 16];
+    uint8_t* scratch = bwd_tc_body<NP>(a, blockIdx.x, gridDim.x, s_trace);
+    grid_arrive_and_wait(a.ctl);
+    const long long t_barrier = clock64();
+    reduce_rows(a, gridDim.x, blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch));
+    grid_depart(a.ctl);
+    dump_trace(a, s_trace, t_barrier);
+}
+
+// Policy and value network of one learner step in ONE launch: CTAs [0, n_pi) take the policy's
+// tiles (partial rows 0 .. n_pi of its workspace), the rest the value function's.  After the grid
+// barrier every CTA helps reduce both sets of rows (the value function's chunks are dealt from
+// the far end so that no CTA gets two chunks of each).  Uses the policy workspace's control words.
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_constant__ BwdTcArgs a_vf,
+                       const int n_pi) {
+    __shared__ long long s_trace[24 * 16];
+    const int n_vf = (int)gridDim.x - n_pi;
+    uint8_t* scratch;
+    if ((int)blockIdx.x < n_pi) scratch = bwd_tc_body<4>(a_pi, blockIdx.x, n_pi, s_trace);
+    else scratch = bwd_tc_body<1>(a_vf, (int)blockIdx.x - n_pi, n_vf, s_trace);
+    grid_arrive_and_wait(a_pi.ctl);
+    const long long t_barrier = clock64();
+    reduce_rows(a_pi, n_pi, blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch));
+    reduce_rows(a_vf, n_vf, (int)gridDim.x - 1 - (int)blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch));
+    grid_depart(a_pi.ctl);
+    dump_trace(a_pi, s_trace, t_barrier);
 }
 
 constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +  // x hi/lo + x^T (2 chunks)
@@ -463,10 +509,9 @@ bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O,
            (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
 }
 
-// Per-CTA partial gradient rows go to ws (same layout as the FP32 kernel), their float64 sum to
-// grad; ctl = two zeroed control words (see the grid barrier in the kernel).
-int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
-                      double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st) {
+namespace {
+BwdTcArgs make_bwd_args(const float* x, const float* params, const float* dout, float* ws, double* grad,
+                        unsigned int* ctl, int M, int O, int H, int N2) {
     BwdTcArgs a{};
     a.x = x, a.params = params, a.dout = dout, a.ws = ws, a.grad = grad, a.ctl = ctl;
     a.M = M, a.O = O, a.H = H, a.N2 = N2;
@@ -474,15 +519,19 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     a.lay = impala_make_layout(O, H, N2);
     const char* tr_env = std::getenv("IMPALA_TC_TRACE");
     a.trace = tr_env && tr_env[0] == '1';
-    static int sms = 0;
+    return a;
+}
+}  // namespace
+
+// Per-CTA partial gradient rows go to ws (same layout as the FP32 kernel), their float64 sum to
+// grad; ctl = two zeroed control words (see the grid barrier in the kernel).
+int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
+                      double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st) {
+    const BwdTcArgs a = make_bwd_args(x, params, dout, ws, grad, ctl, M, O, H, N2);
     static bool opted[2] = {false, false};
     cudaError_t e;
-    if (!sms) {
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
-            return (int)e;
-    }
+    int sms = 0;
+    if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
     const int which = N2 == 1 ? 0 : 1;
     auto kernel = which ? mlp_bwd_tc_kernel<4> : mlp_bwd_tc_kernel<1>;
     if (!opted[which]) {
@@ -490,9 +539,36 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
         if (e != cudaSuccess) return (int)e;
         opted[which] = true;
     }
-    int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    int grid = a.num_tiles < sms ? a.num_tiles : sms;  // <= SM count: the grid barrier needs residency
     if (grid > kMaxParts) grid = kMaxParts;
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+    return impala_launch_status();
+}
+
+// Both networks in one launch; the caller has checked eligibility of each and 2 <= A <= 4.
+int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* params_vf,
+                           const float* dlogits, const float* dv, float* ws_pi, float* ws_vf,
+                           double* grad_pi, double* grad_vf, unsigned int* ctl, int M_pi, int M_vf, int O,
+                           int H_pi, int H_vf, int A, cudaStream_t st) {
+    const BwdTcArgs a_pi = make_bwd_args(x, params_pi, dlogits, ws_pi, grad_pi, ctl, M_pi, O, H_pi, A);
+    const BwdTcArgs a_vf = make_bwd_args(x, params_vf, dv, ws_vf, grad_vf, ctl, M_vf, O, H_vf, 1);
+    static bool opted = false;
+    cudaError_t e;
+    int sms = 0;
+    if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
+    if (!opted) {
+        e = cudaFuncSetAttribute(mlp_bwd_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        opted = true;
+    }
+    const int total_tiles = a_pi.num_tiles + a_vf.num_tiles;
+    int grid = total_tiles < sms ? total_tiles : sms;
+    if (grid > kMaxParts) grid = kMaxParts;
+    const int n_pi = impala_pair_split(a_pi.num_tiles, a_vf.num_tiles, grid,
+                                       impala_env_int("IMPALA_PAIR_W_BWD", 127) * (H_pi / 128),
+                                       100 * (H_vf / 128));
+    mlp_bwd_tc_pair_kernel<<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi);
     return impala_launch_status();
 }
 

@@ -34,10 +34,20 @@ bool impala_mlp_fwd_tc_eligible(const float* x, int M, int O, int H, int N2);
 int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, int O, int H, int N2,
                       cudaStream_t st);
 
-// Tensor-core backward (mlp_bwd_tc.cu): per-CTA partial rows into ws, *grid_out rows written.
+// Policy + value network in one launch (CTA ranges per network); A in 2..4, both nets eligible.
+int impala_mlp_fwd_tc_pair(const float* x, const float* params_pi, const float* params_vf, float* logits,
+                           float* values, int M_pi, int M_vf, int O, int H_pi, int H_vf, int A,
+                           cudaStream_t st);
+
+// Tensor-core backward (mlp_bwd_tc.cu): per-CTA partial rows into ws, reduced in-kernel to grad.
 bool impala_mlp_bwd_tc_eligible(const float* x, const float* dout, int M, int O, int H, int N2);
 int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
                       double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st);
+
+int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* params_vf,
+                           const float* dlogits, const float* dv, float* ws_pi, float* ws_vf,
+                           double* grad_pi, double* grad_vf, unsigned int* ctl, int M_pi, int M_vf, int O,
+                           int H_pi, int H_vf, int A, cudaStream_t st);
 
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \

@@ -230,10 +230,9 @@ class LearnerEngine:
         g_vf = C.c_void_p(self.comm.data_ptr() + 8 * self.n_pi)
         scal = C.c_void_p(self.comm.data_ptr() + 8 * self.n_total)
         obs = _ptr(d["obs"])
-        _cabi.check(lib.impala_mlp_forward(obs, p_pi, _ptr(self.logits), self.M_pi, O, self.H_pi, A, st),
-                    "impala_mlp_forward(policy)")
-        _cabi.check(lib.impala_mlp_forward(obs, p_vf, _ptr(self.values), self.M_vf, O, self.H_v, 1, st),
-                    "impala_mlp_forward(value_fn)")
+        _cabi.check(lib.impala_mlp_forward_pair(obs, p_pi, p_vf, _ptr(self.logits), _ptr(self.values),
+                                                self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
+                    "impala_mlp_forward_pair")
         _cabi.check(lib.impala_vtrace_loss(
             _ptr(self.logits), _ptr(d["beh_logits"]), _ptr(d["actions"]),
             _ptr(d["rewards"]), _ptr(d["done"]), _ptr(d["lens"]), _ptr(self.values),
@@ -242,22 +241,27 @@ class LearnerEngine:
             float(hp.gamma), float(hp.rho_bar), float(hp.c_bar), float(hp.v_loss_c),
             float(hp.policy_loss_c), float(hp.entropy_c), float(self.inv_batch), self.mode, st),
             "impala_vtrace_loss")
-        _cabi.check(lib.impala_mlp_backward(obs, p_pi, _ptr(self.dlogits), g_pi, _ptr(self.ws_pi),
-                                            self.ws_pi_bytes, self.M_pi, O, self.H_pi, A, st),
-                    "impala_mlp_backward(policy)")
-        _cabi.check(lib.impala_mlp_backward(obs, p_vf, _ptr(self.dv), g_vf, _ptr(self.ws_vf),
-                                            self.ws_vf_bytes, self.M_vf, O, self.H_v, 1, st),
-                    "impala_mlp_backward(value_fn)")
-        return 3 + self._bwd_launches(self.H_pi, A) + self._bwd_launches(self.H_v, 1)
+        _cabi.check(lib.impala_mlp_backward_pair(
+            obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), g_pi, g_vf, _ptr(self.ws_pi), self.ws_pi_bytes,
+            _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
+            "impala_mlp_backward_pair")
+        return 1 + self._mlp_launches()
 
-    def _bwd_launches(self, H: int, N2: int) -> int:
-        """Kernels behind one impala_mlp_backward call: the tensor-core kernel reduces its per-CTA
-        partial rows itself, the FP32 kernel is followed by a reduction launch (csrc/mlp.cu)."""
+    def _mlp_launches(self) -> int:
+        """Kernels behind the forward pair + backward pair calls (csrc/mlp.cu): one launch each where
+        the tensor-core path covers both networks; otherwise per network one forward and one
+        backward (+ a reduction launch after an FP32 backward)."""
         import os
 
-        tc = (os.environ.get("IMPALA_MLP_TC", "1")[:1] != "0" and self.O % 4 == 0 and 4 <= self.O <= 28
-              and H in (128, 256) and N2 <= 4)
-        return 1 if tc else 2
+        env = os.environ.get
+        tc = env("IMPALA_MLP_TC", "1")[:1] != "0"
+        fwd_ok = lambda H, N2: tc and self.O % 4 == 0 and 4 <= self.O <= 28 and 16 <= H <= 256 and H % 32 == 0 and N2 <= 4
+        bwd_ok = lambda H, N2: tc and self.O % 4 == 0 and 4 <= self.O <= 28 and H in (128, 256) and N2 <= 4
+        pair = env("IMPALA_MLP_PAIR", "1")[:1] != "0" and 2 <= self.A <= 4
+        nets = ((self.H_pi, self.A), (self.H_v, 1))
+        fwd = 1 if pair and all(fwd_ok(H, n) for H, n in nets) else 2
+        bwd = 1 if pair and all(bwd_ok(H, n) for H, n in nets) else sum(1 if bwd_ok(H, n) else 2 for H, n in nets)
+        return fwd + bwd
 
     def _enqueue_opt(self) -> int:
         hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -76,6 +76,35 @@ def mlp_backward(x, params, dout, O: int, H: int, N2: int):
     return grad
 
 
+def mlp_forward_pair(x, params_pi, params_vf, M_pi: int, M_vf: int, O: int, H_pi: int, H_vf: int, A: int):
+    """Policy logits on the first M_pi rows of x and values on the first M_vf rows, one call."""
+    _need_cuda(x, params_pi, params_vf)
+    logits = torch.empty(M_pi, A, dtype=torch.float32, device=x.device)
+    values = torch.empty(M_vf, dtype=torch.float32, device=x.device)
+    _cabi.check(_cabi.lib().impala_mlp_forward_pair(_p(x), _p(params_pi), _p(params_vf), _p(logits), _p(values),
+                                                    M_pi, M_vf, O, H_pi, H_vf, A, _st()),
+                "impala_mlp_forward_pair")
+    return logits, values
+
+
+def mlp_backward_pair(x, params_pi, params_vf, dlogits, dv, O: int, H_pi: int, H_vf: int, A: int):
+    _need_cuda(x, params_pi, params_vf, dlogits, dv)
+    lib = _cabi.lib()
+    M_pi, M_vf = dlogits.numel() // A, dv.numel()
+    out, wss = [], []
+    for M, H, N2 in ((M_pi, H_pi, A), (M_vf, H_vf, 1)):
+        nbytes = lib.impala_mlp_backward_workspace(M, O, H, N2)
+        if nbytes < 0:
+            _cabi.check(int(nbytes), "impala_mlp_backward_workspace")
+        wss.append(torch.zeros(int(nbytes), dtype=torch.uint8, device=x.device))
+        out.append(torch.empty(_cabi.param_layout(O, H, N2)[1], dtype=torch.float64, device=x.device))
+    _cabi.check(lib.impala_mlp_backward_pair(_p(x), _p(params_pi), _p(params_vf), _p(dlogits), _p(dv),
+                                             _p(out[0]), _p(out[1]), _p(wss[0]), wss[0].numel(), _p(wss[1]),
+                                             wss[1].numel(), M_pi, M_vf, O, H_pi, H_vf, A, _st()),
+                "impala_mlp_backward_pair")
+    return out[0], out[1]
+
+
 def vtrace(cur_logits, beh_logits, actions, rewards, done, lens, v, gamma, rho_bar, c_bar,
            mode="reference"):
     _need_cuda(cur_logits, beh_logits, actions, rewards, done, lens, v)
