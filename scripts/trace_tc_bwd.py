@@ -10,14 +10,20 @@ import torch  # noqa: E402
 
 from torched_impala_b200 import _cabi, ops, synth  # noqa: E402
 
-M, O, H, N2 = 86016, 24, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 1
+PAIR = len(sys.argv) > 1 and sys.argv[1] == "pair"  # c4 pair launch: CTA 0 is a policy CTA
+M, O, H, N2 = 86016, 24, 256, 4 if PAIR else (int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 rng = np.random.default_rng(0)
 p = synth.init_params(0, O, N2, H)["policy"]
 x = torch.from_numpy(rng.standard_normal((M, O), dtype=np.float32)).cuda()
 d = torch.from_numpy(rng.standard_normal((M, N2), dtype=np.float32)).cuda()
 pp = ops.pack_params(p)
+pv = ops.pack_params(synth.init_params(1, O, 1, H)["policy"])
+dv = torch.from_numpy(rng.standard_normal((M,), dtype=np.float32)).cuda()
 for _ in range(3):
-    ops.mlp_backward(x, pp, d, O, H, N2)
+    if PAIR:
+        ops.mlp_backward_pair(x, pp, pv, d[:81920], dv, O, H, H, 4)
+    else:
+        ops.mlp_backward(x, pp, d, O, H, N2)
 torch.cuda.synchronize()
 fn = _cabi.lib().impala_debug_read_trace
 fn.restype = C.c_int
@@ -27,7 +33,7 @@ t = np.array(buf[:], dtype=np.int64).reshape(24, 16)
 t0 = t[0, 15]
 names = ["E.begin", "E.d1_full", "E.math_done", "E.lo_free", "E.dp_full", "P.begin", "P.raw_ok", "P.empty_ok",
          "P.full", "M1.begin", "M1.ready", "M1.issued", "M2.ready", "M2.issued"]
-print("kernel cycles (CTA 0):", t[1, 15] - t0)
+print("kernel cycles (CTA 0):", t[1, 15] - t0, " grid barrier passed at:", t[2, 15] - t0)
 print("tile " + " ".join(f"{n:>11s}" for n in names))
 for i in range(24):
     if t[i, :14].any():

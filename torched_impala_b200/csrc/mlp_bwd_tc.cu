@@ -336,16 +336,23 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             tc::tc_fence_after();
             TRACE(i, 10)
             if (tc::elect_one()) {
-                const uint64_t so = static_cast<uint64_t>((s * kXTileBytes) >> 4);
-#pragma unroll 1
-                for (int b = 0; b < nblk; ++b) {
-                    const uint32_t d = tmem_base + d1 * 128 + b * 64;
-#pragma unroll 1
-                    for (int kk = 0; kk < ksteps1; ++kk) {
-                        const uint64_t ko = 2 * kk, bo = b * kBlkOff;
-                        tc::umma_tf32(d, dw_hi + bo + ko, dx_hi + so + ko, idesc1, kk > 0);
-                        tc::umma_tf32(d, dw_lo + bo + ko, dx_hi + so + ko, idesc1, true);
-                        tc::umma_tf32(d, dw_hi + bo + ko, dx_lo + so + ko, idesc1, true);
+                // fully unrolled with uniform guards: descriptor arithmetic folds to constants
+                // off two per-tile bases (the rolled loop spent ~12 issue slots per UMMA)
+                const uint64_t xh = dx_hi + static_cast<uint64_t>((s * kXTileBytes) >> 4);
+                const uint64_t xl = dx_lo + static_cast<uint64_t>((s * kXTileBytes) >> 4);
+                const uint32_t d0 = tmem_base + d1 * 128;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    if (b < nblk) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < ksteps1) {
+                                const uint64_t ko = 2 * kk, bo = b * kBlkOff;
+                                tc::umma_tf32(d0 + b * 64, dw_hi + bo + ko, xh + ko, idesc1, kk > 0);
+                                tc::umma_tf32(d0 + b * 64, dw_lo + bo + ko, xh + ko, idesc1, true);
+                                tc::umma_tf32(d0 + b * 64, dw_hi + bo + ko, xl + ko, idesc1, true);
+                            }
+                        }
                     }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
@@ -361,17 +368,20 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             tc::tc_fence_after();
             TRACE(i, 12)
             if (tc::elect_one()) {
-#pragma unroll 1
-                for (int b = 0; b < nblk; ++b) {
-                    const uint32_t d = tmem_base + kColAcc + b * 64;
-                    const uint32_t a_hi = tmem_base + d1 * 128 + b * 64, a_lo = tmem_base + kColLo + b * 64;
-#pragma unroll 1
-                    for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
-                        // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
-                        const uint64_t ko = static_cast<uint64_t>(
-                            (((2 * s + (kk >> 2)) * kXTileBytes) + (kk & 3) * 32) >> 4);
-                        tc::umma_tf32_ts(d, a_hi + 8 * kk, dxt + ko, idesc2w, i > 0 || kk > 0);
-                        tc::umma_tf32_ts(d, a_lo + 8 * kk, dxt + ko, idesc2, true);
+                const uint64_t xts = dxt + static_cast<uint64_t>((2 * s * kXTileBytes) >> 4);
+                const uint32_t a_hi0 = tmem_base + d1 * 128, a_lo0 = tmem_base + kColLo, acc0 = tmem_base + kColAcc;
+                const uint32_t first = i > 0;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    if (b < nblk) {
+#pragma unroll
+                        for (int kk = 0; kk < kRowsT / 8; ++kk) {  // K = 64 batch rows, 8 per step
+                            // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
+                            constexpr int kChunk16 = kXTileBytes >> 4;
+                            const uint64_t ko = static_cast<uint64_t>((kk >> 2) * kChunk16 + (kk & 3) * 2);
+                            tc::umma_tf32_ts(acc0 + b * 64, a_hi0 + b * 64 + 8 * kk, xts + ko, idesc2w, first | (kk > 0));
+                            tc::umma_tf32_ts(acc0 + b * 64, a_lo0 + b * 64 + 8 * kk, xts + ko, idesc2, true);
+                        }
                     }
                 }
                 tc::umma_commit(&bars->lo_free);   // DP_lo region reusable
