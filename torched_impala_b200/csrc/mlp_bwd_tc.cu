@@ -144,13 +144,16 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         const int blk = warp >> 2, q = warp & 3, jl = 32 * q + lane, j = 128 * blk + jl;
         float gb2 = 0.f;
         if (blk < nblk) {
-            float w2r[NP], gw2[NP];
+            // Two batch rows per step in packed fp32 pairs (.x = even row, .y = odd row).
+            float2 w2p[NP], gw2p[NP];
             const float b1j = __ldg(b1 + j);
-            float gb1 = 0.f;
+            const float2 b1p = make_float2(b1j, b1j);
+            float2 gb1p = make_float2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
-                w2r[n] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
-                gw2[n] = 0.f;
+                const float w = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
+                w2p[n] = make_float2(w, w);
+                gw2p[n] = make_float2(0.f, 0.f);
             }
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
             for (int i = 0; i < n_my; ++i) {
@@ -163,9 +166,9 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
                 TRACE(i, 1)
-                const float* dz_tile = dzs + s * kRowsT * NP;
+                const float* dz_tile = dzs + s * kRowsT * NP;  // [row pair][n][2]
                 if (tid < a.N2) {
-                    for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[r * NP + tid];
+                    for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[((r >> 1) * NP + tid) * 2 + (r & 1)];
                 }
                 float lo[2][32];
 #pragma unroll
@@ -173,24 +176,32 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                     float v[32];
                     tc::tmem_ld32(c_hi + 32 * hh, v);
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        float dz[NP];
+                    for (int pr = 0; pr < 16; ++pr) {
+                        const float* zp = dz_tile + (16 * hh + pr) * 2 * NP;
+                        float2 dz[NP];
                         if constexpr (NP == 4) {
-                            const float4 t = *reinterpret_cast<const float4*>(dz_tile + (32 * hh + r) * 4);
-                            dz[0] = t.x, dz[1] = t.y, dz[2] = t.z, dz[3] = t.w;
+                            const float4 t0 = *reinterpret_cast<const float4*>(zp);
+                            const float4 t1 = *reinterpret_cast<const float4*>(zp + 4);
+                            dz[0] = make_float2(t0.x, t0.y), dz[1] = make_float2(t0.z, t0.w);
+                            dz[2] = make_float2(t1.x, t1.y), dz[3] = make_float2(t1.z, t1.w);
                         } else {
-                            dz[0] = dz_tile[32 * hh + r];
+                            dz[0] = *reinterpret_cast<const float2*>(zp);
                         }
-                        const float pre = v[r] + b1j, h = fmaxf(pre, 0.f);
-                        float dh = 0.f;
+                        const float2 pre = tc::fadd2(make_float2(v[2 * pr], v[2 * pr + 1]), b1p);
+                        const float2 h = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
+                        float2 dh = tc::fmul2(dz[0], w2p[0]);
 #pragma unroll
-                        for (int n = 0; n < NP; ++n) {
-                            dh = fmaf(dz[n], w2r[n], dh);
-                            gw2[n] = fmaf(dz[n], h, gw2[n]);
-                        }
-                        const float dp = pre > 0.f ? dh : 0.f;  // relu'(0) = 0 as in torch
-                        gb1 += dp;
-                        tc::split_tf32(dp, v[r], lo[hh][r]);
+                        for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
+                        // relu'(0) = 0 as in torch
+                        const float2 dp = make_float2(pre.x > 0.f ? dh.x : 0.f, pre.y > 0.f ? dh.y : 0.f);
+                        gb1p = tc::fadd2(gb1p, dp);
+                        float2 hi;
+                        hi.x = tc::round_tf32(dp.x), hi.y = tc::round_tf32(dp.y);
+                        const float2 l = tc::fsub2(dp, hi);  // exact
+                        v[2 * pr] = hi.x, v[2 * pr + 1] = hi.y;
+                        lo[hh][2 * pr] = l.x, lo[hh][2 * pr + 1] = l.y;
                     }
                     tc::tmem_st32(c_hi + 32 * hh, v);  // DP_hi replaces PRE in place
                 }
@@ -218,10 +229,10 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 if (c < ochunks) wrow[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-            wsb[a.lay.ob1 + j] = gb1;
+            wsb[a.lay.ob1 + j] = gb1p.x + gb1p.y;
 #pragma unroll
             for (int n = 0; n < NP; ++n)
-                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = gw2[n];
+                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = gw2p[n].x + gw2p[n].y;
             if (tid < a.N2) wsb[a.lay.ob2 + tid] = gb2;
         }
         // pads of the partial row (all 256 epilogue threads)
@@ -311,7 +322,8 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 }
             }
 #pragma unroll
-            for (int n = 0; n < NP; ++n) dzs[(s * kRowsT + r) * NP + n] = z[n];
+            for (int n = 0; n < NP; ++n)  // [row pair][n][2]: the epilogue reads pairs of rows
+                dzs[((s * (kRowsT / 2) + (r >> 1)) * NP + n) * 2 + (r & 1)] = z[n];
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
             TRACE(i, 8)

@@ -210,11 +210,47 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ------------------------------------------------------------------ 3xTF32 operand split
 // hi = round-to-nearest tf32 of x (what the tensor core will see exactly), lo = x - hi (exact in
 // fp32; the tensor core truncates it to tf32, an error of 2^-21 relative to x).
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    return __uint_as_float(h);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
     hi = __uint_as_float(h);
     lo = x - hi;
+}
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot for two lanes of a
+// 64-bit register pair - the epilogues are issue-bound, so this is where their time goes.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)),
+          "l"(*reinterpret_cast<uint64_t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
 }
 // byte offset of 16-byte chunk `c16` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c16) {
