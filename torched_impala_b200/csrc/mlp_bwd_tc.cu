@@ -28,10 +28,13 @@
 //
 // TMEM map (512 columns): [0,256) two PRE/DP_hi buffers x (2 hidden blocks x 64 rows),
 //                         [256,384) DP_lo, [384,512) dW1' accumulators (2 blocks x (32 + 32)).
-// Warp roles (352 threads, one persistent CTA per SM):
-//   warps 0-7   epilogue: thread = hidden unit j (TMEM lane j % 128, block j / 128)
-//   warps 8-9   producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo tiles
-//   warp  10    TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
+// Warp roles (608 threads, one persistent CTA per SM):
+//   warps 0-15  epilogue: thread = (hidden unit j, half of the tile's 64 batch rows); TMEM lane
+//               j % 128, block j / 128.  The epilogue is latency-bound, so four warps per SM
+//               sub-partition (instead of two with 64 rows per thread) is what keeps it off the
+//               critical path; the two halves' dW2 / db1 sums meet in shared memory at the end
+//   warps 16-17 producer: TMA bulk copies of raw x / dout rows (4-deep ring) -> hi/lo tiles; db2
+//   warp  18    TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
 //
 // Cross-CTA reduction: every CTA writes its float32 partial gradient row, the grid meets at an
 // arrival counter (grid <= SM count and one CTA per SM, so all CTAs are co-resident), and CTA c
@@ -54,7 +57,9 @@ constexpr int kRowsT = 64;       // batch rows per tile: N of UMMA1, K of UMMA2
 constexpr int kKPad = 32;        // padded feature count K' (data + bias column + zeros)
 constexpr int kXStages = 3;      // converted x / x^T / dz stages
 constexpr int kRawStages = 4;    // bulk-copy ring depth
-constexpr int kThreads = 11 * 32;
+constexpr int kWarps = 19;
+constexpr int kThreads = kWarps * 32;
+constexpr int kEpiThreads = 16 * 32;
 constexpr int kWTileBytes = 256 * 128;      // 256 hidden rows x 128 B
 constexpr int kXTileBytes = kRowsT * 128;   // 8 KiB: 64 rows x 128 B (also 2 x [32 rows x 128 B])
 constexpr int kRawStageBytes = 8192;        // x rows (<= 64*28*4 = 7168 B) | dout rows at +7168
@@ -77,6 +82,7 @@ struct BwdTcArgs {
 struct __align__(8) Barriers {
     uint64_t raw_full[kRawStages], full[kXStages], empty[kXStages];
     uint64_t d1_full[2], dp_full[2], lo_free, done;
+    float gb2_part[4];
     uint32_t tmem_base;
 };
 
@@ -99,7 +105,8 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     uint8_t* xt = x_lo + kXStages * kXTileBytes;
     uint8_t* raw = xt + 2 * kXStages * kXTileBytes;   // kRawStages x 8 KiB
     float* dzs = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [kXStages][64][NP]
-    Barriers* bars = reinterpret_cast<Barriers*>(dzs + kXStages * kRowsT * NP);
+    float* exch = dzs + kXStages * kRowsT * NP;  // [NP + 1][256]: dW2 / db1 sums of the odd half
+    Barriers* bars = reinterpret_cast<Barriers*>(exch + (NP + 1) * 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* __restrict__ W1 = a.params + a.lay.oW1;
@@ -107,7 +114,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     const float* __restrict__ W2 = a.params + a.lay.oW2;
     const int O = a.O, H = a.H, ochunks = O >> 2, nblk = H >> 7;
     const int n_my = (a.num_tiles - cta + ncta - 1) / ncta;
-    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 10);
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 18);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
     if (a.trace && blockIdx.x == 0)
@@ -117,7 +124,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     // ---- one-time setup
     tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/false);
     tc::fence_proxy_async();
-    if (warp == 10) {
+    if (warp == 18) {
         tc::tmem_alloc(&bars->tmem_base, 512);
         if (lane == 0) {
             for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
@@ -127,7 +134,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             }
             for (int s = 0; s < 2; ++s) {
                 tc::mbar_init(&bars->d1_full[s], 1);           // tcgen05.commit after UMMA1
-                tc::mbar_init(&bars->dp_full[s], nblk * 128);  // every active epilogue thread
+                tc::mbar_init(&bars->dp_full[s], nblk * 256);  // every active epilogue thread
             }
             tc::mbar_init(&bars->lo_free, 1);  // tcgen05.commit after UMMA2
             tc::mbar_init(&bars->done, 1);
@@ -139,83 +146,89 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     tc::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < 8) {
+    if (warp < 16) {
         // =============================== epilogue ===============================
-        const int blk = warp >> 2, q = warp & 3, jl = 32 * q + lane, j = 128 * blk + jl;
-        float gb2 = 0.f;
+        const int hh = warp >> 3, blk = (warp >> 2) & 1, q = warp & 3;  // row half, hidden block, lane quarter
+        const int jl = 32 * q + lane, j = 128 * blk + jl;
+        // Two batch rows per step in packed fp32 pairs (.x = even row, .y = odd row).
+        float2 w2p[NP], gw2p[NP];
+        float2 gb1p = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NP; ++n) gw2p[n] = make_float2(0.f, 0.f);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
         if (blk < nblk) {
-            // Two batch rows per step in packed fp32 pairs (.x = even row, .y = odd row).
-            float2 w2p[NP], gw2p[NP];
             const float b1j = __ldg(b1 + j);
             const float2 b1p = make_float2(b1j, b1j);
-            float2 gb1p = make_float2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
                 const float w = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
                 w2p[n] = make_float2(w, w);
-                gw2p[n] = make_float2(0.f, 0.f);
             }
-            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % kXStages, ph = (i / kXStages) & 1;
                 const int d1 = i & 1, dph = (i >> 1) & 1;
-                const uint32_t c_hi = lane_addr + d1 * 128 + blk * 64;   // PRE in, DP_hi out
-                const uint32_t c_lo = lane_addr + kColLo + blk * 64;
+                const uint32_t c_hi = lane_addr + d1 * 128 + blk * 64 + 32 * hh;   // PRE in, DP_hi out
+                const uint32_t c_lo = lane_addr + kColLo + blk * 64 + 32 * hh;
                 TRACE(i, 0)
                 tc::mbar_wait(&bars->full[s], ph);       // dz rows of this tile are visible
                 tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
                 TRACE(i, 1)
-                const float* dz_tile = dzs + s * kRowsT * NP;  // [row pair][n][2]
-                if (tid < a.N2) {
-                    for (int r = 0; r < kRowsT; ++r) gb2 += dz_tile[((r >> 1) * NP + tid) * 2 + (r & 1)];
-                }
-                float lo[2][32];
+                const float* dz_half = dzs + (s * kRowsT + 32 * hh) * NP;  // [row pair][n][2]
+                float v[32], lo[32];
+                tc::tmem_ld32(c_hi, v);
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {  // two halves of 32 batch rows
-                    float v[32];
-                    tc::tmem_ld32(c_hi + 32 * hh, v);
-#pragma unroll
-                    for (int pr = 0; pr < 16; ++pr) {
-                        const float* zp = dz_tile + (16 * hh + pr) * 2 * NP;
-                        float2 dz[NP];
-                        if constexpr (NP == 4) {
-                            const float4 t0 = *reinterpret_cast<const float4*>(zp);
-                            const float4 t1 = *reinterpret_cast<const float4*>(zp + 4);
-                            dz[0] = make_float2(t0.x, t0.y), dz[1] = make_float2(t0.z, t0.w);
-                            dz[2] = make_float2(t1.x, t1.y), dz[3] = make_float2(t1.z, t1.w);
-                        } else {
-                            dz[0] = *reinterpret_cast<const float2*>(zp);
-                        }
-                        const float2 pre = tc::fadd2(make_float2(v[2 * pr], v[2 * pr + 1]), b1p);
-                        const float2 h = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
-                        float2 dh = tc::fmul2(dz[0], w2p[0]);
-#pragma unroll
-                        for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
-#pragma unroll
-                        for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
-                        // relu'(0) = 0 as in torch
-                        const float2 dp = make_float2(pre.x > 0.f ? dh.x : 0.f, pre.y > 0.f ? dh.y : 0.f);
-                        gb1p = tc::fadd2(gb1p, dp);
-                        float2 hi;
-                        hi.x = tc::round_tf32(dp.x), hi.y = tc::round_tf32(dp.y);
-                        const float2 l = tc::fsub2(dp, hi);  // exact
-                        v[2 * pr] = hi.x, v[2 * pr + 1] = hi.y;
-                        lo[hh][2 * pr] = l.x, lo[hh][2 * pr + 1] = l.y;
+                for (int pr = 0; pr < 16; ++pr) {
+                    const float* zp = dz_half + pr * 2 * NP;
+                    float2 dz[NP];
+                    if constexpr (NP == 4) {
+                        const float4 t0 = *reinterpret_cast<const float4*>(zp);
+                        const float4 t1 = *reinterpret_cast<const float4*>(zp + 4);
+                        dz[0] = make_float2(t0.x, t0.y), dz[1] = make_float2(t0.z, t0.w);
+                        dz[2] = make_float2(t1.x, t1.y), dz[3] = make_float2(t1.z, t1.w);
+                    } else {
+                        dz[0] = *reinterpret_cast<const float2*>(zp);
                     }
-                    tc::tmem_st32(c_hi + 32 * hh, v);  // DP_hi replaces PRE in place
+                    const float2 pre = tc::fadd2(make_float2(v[2 * pr], v[2 * pr + 1]), b1p);
+                    // relu and relu' as one 0/1 mask (FSET) and packed multiplies; relu'(0) = 0 as
+                    // in torch
+                    const float2 m = make_float2(pre.x > 0.f ? 1.f : 0.f, pre.y > 0.f ? 1.f : 0.f);
+                    const float2 h = tc::fmul2(pre, m);
+                    float2 dh = tc::fmul2(dz[0], w2p[0]);
+#pragma unroll
+                    for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
+                    const float2 dp = tc::fmul2(dh, m);
+                    gb1p = tc::fadd2(gb1p, dp);
+                    // hi = dp truncated to tf32 (one LOP3; cvt.rna.tf32 is a 4-instruction
+                    // sequence on sm_100), lo = the exact remainder < 2^-10 |dp|
+                    float2 hi;
+                    hi.x = __uint_as_float(__float_as_uint(dp.x) & 0xffffe000u);
+                    hi.y = __uint_as_float(__float_as_uint(dp.y) & 0xffffe000u);
+                    const float2 l = tc::fsub2(dp, hi);
+                    v[2 * pr] = hi.x, v[2 * pr + 1] = hi.y;
+                    lo[2 * pr] = l.x, lo[2 * pr + 1] = l.y;
                 }
+                tc::tmem_st32(c_hi, v);  // DP_hi replaces PRE in place
                 TRACE(i, 2)
                 tc::mbar_wait(&bars->lo_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
                 tc::tc_fence_after();
                 TRACE(i, 3)
-                tc::tmem_st32(c_lo, lo[0]);
-                tc::tmem_st32(c_lo + 32, lo[1]);
+                tc::tmem_st32(c_lo, lo);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars->dp_full[d1]);
                 TRACE(i, 4)
             }
+            if (hh == 1) {  // hand this half's sums to the thread that owns the other half
+                exch[j] = gb1p.x + gb1p.y;
+#pragma unroll
+                for (int n = 0; n < NP; ++n) exch[(n + 1) * 256 + j] = gw2p[n].x + gw2p[n].y;
+            }
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");  // all 16 epilogue warps
+        if (blk < nblk && hh == 0) {
             // ---- read out dW1' (TMEM) and write this CTA's partial gradient row
             tc::mbar_wait(&bars->done, 0);
             tc::tc_fence_after();
@@ -229,24 +242,26 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 if (c < ochunks) wrow[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-            wsb[a.lay.ob1 + j] = gb1p.x + gb1p.y;
+            wsb[a.lay.ob1 + j] = (gb1p.x + gb1p.y) + exch[j];
 #pragma unroll
             for (int n = 0; n < NP; ++n)
-                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = gw2p[n].x + gw2p[n].y;
-            if (tid < a.N2) wsb[a.lay.ob2 + tid] = gb2;
+                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = (gw2p[n].x + gw2p[n].y) + exch[(n + 1) * 256 + j];
         }
-        // pads of the partial row (all 256 epilogue threads)
+        // pads of the partial row (all epilogue threads)
         {
             float* wsb = a.ws + (size_t)cta * a.lay.total;
             const int64_t lo4[4] = {a.lay.oW1 + (int64_t)H * O, a.lay.ob1 + H,
                                     a.lay.oW2 + (int64_t)a.N2 * H, a.lay.ob2 + a.N2};
             const int64_t hi4[4] = {a.lay.ob1, a.lay.oW2, a.lay.ob2, a.lay.total};
             for (int sgm = 0; sgm < 4; ++sgm)
-                for (int64_t p = lo4[sgm] + tid; p < hi4[sgm]; p += 256) wsb[p] = 0.f;
+                for (int64_t p = lo4[sgm] + tid; p < hi4[sgm]; p += kEpiThreads) wsb[p] = 0.f;
         }
-    } else if (warp < 10) {
+    } else if (warp < 18) {
         // ===================== producer (2 warps, 32 rows of the tile each) =====================
-        const int pw = warp - 8, r = 32 * pw + lane;  // row of the tile this thread converts
+        const int pw = warp - 16, r = 32 * pw + lane;  // row of the tile this thread converts
+        float gb2[NP];  // db2 = column sums of dout: this thread's rows, combined at the end
+#pragma unroll
+        for (int n = 0; n < NP; ++n) gb2[n] = 0.f;
         const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
         auto tile_of = [&](int i) { return cta + i * ncta; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kRowsT <= a.M; };
@@ -322,11 +337,30 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 }
             }
 #pragma unroll
-            for (int n = 0; n < NP; ++n)  // [row pair][n][2]: the epilogue reads pairs of rows
+            for (int n = 0; n < NP; ++n) {  // [row pair][n][2]: the epilogue reads pairs of rows
                 dzs[((s * (kRowsT / 2) + (r >> 1)) * NP + n) * 2 + (r & 1)] = z[n];
+                gb2[n] += z[n];
+            }
             tc::fence_proxy_async();
             tc::mbar_arrive(&bars->full[s]);
             TRACE(i, 8)
+        }
+        // db2: fixed-order tree over the 64 producer threads
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) gb2[n] += __shfl_xor_sync(0xffffffffu, gb2[n], off);
+        }
+        if (pw == 1 && lane == 0) {
+#pragma unroll
+            for (int n = 0; n < NP; ++n) bars->gb2_part[n] = gb2[n];
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (pw == 0 && lane == 0) {
+            float* wsb = a.ws + (size_t)cta * a.lay.total;
+#pragma unroll
+            for (int n = 0; n < NP; ++n)
+                if (n < a.N2) wsb[a.lay.ob2 + n] = gb2[n] + bars->gb2_part[n];
         }
     } else {
         // =============================== UMMA issuer ===============================
@@ -410,7 +444,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     tc::tc_fence_before();
     __threadfence();  // this thread's partial-row stores are visible device-wide
     __syncthreads();
-    if (warp == 10) {
+    if (warp == 18) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
@@ -442,7 +476,7 @@ __device__ __forceinline__ void grid_depart(unsigned int* ctl) {
 }
 
 // Deterministic float64 sum of `nparts` partial rows: chunk c = entries [64c, 64c + 64); this CTA
-// takes chunks first, first + stride, ...; warp w adds rows w, w + 11, ... and warp 0 combines.
+// takes chunks first, first + stride, ...; warp w adds rows w, w + kWarps, ... and warp 0 combines.
 __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts, const int first,
                                             const int stride, double* s_red) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -454,15 +488,15 @@ __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts
         if (e0 < total) {
             const float* col = a.ws + e0;
             int p = warp;
-            for (; p + 3 * 11 < nparts; p += 4 * 11) {
+            for (; p + 3 * kWarps < nparts; p += 4 * kWarps) {
                 const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
-                const float2 v1 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 11) * total));
-                const float2 v2 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 22) * total));
-                const float2 v3 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 33) * total));
+                const float2 v1 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + kWarps) * total));
+                const float2 v2 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 2 * kWarps) * total));
+                const float2 v3 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)(p + 3 * kWarps) * total));
                 sx += v0.x, sy += v0.y, sx += v1.x, sy += v1.y;
                 sx += v2.x, sy += v2.y, sx += v3.x, sy += v3.y;
             }
-            for (; p < nparts; p += 11) {
+            for (; p < nparts; p += kWarps) {
                 const float2 v0 = __ldcg(reinterpret_cast<const float2*>(col + (size_t)p * total));
                 sx += v0.x, sy += v0.y;
             }
@@ -473,7 +507,7 @@ __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts
         if (warp == 0 && e0 < total) {
             double tx = 0.0, ty = 0.0;
 #pragma unroll
-            for (int w = 0; w < 11; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
+            for (int w = 0; w < kWarps; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
             *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
         }
         __syncthreads();
@@ -521,7 +555,7 @@ mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_cons
 
 constexpr size_t kSmemBytes = 1024 + 2 * kWTileBytes + 4 * kXStages * kXTileBytes +  // x hi/lo + x^T (2 chunks)
                               kRawStages * kRawStageBytes + kXStages * kRowsT * 4 * sizeof(float) +
-                              sizeof(Barriers);
+                              5 * 256 * sizeof(float) + sizeof(Barriers);
 
 }  // namespace
 
