@@ -11,13 +11,14 @@
 // once: the epilogue thread that owns TMEM lane r applies ReLU and the tiny second layer
 // (<= 4 outputs) in registers and writes the row of logits / the value.
 //
-// Warp roles (416 threads, one persistent CTA per SM):
-//   warps 0-7  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast) -> global; two
-//              warps per TMEM lane quarter, each taking half of the hidden columns (partial sums
-//              meet in shared memory)
-//   warps 8-11 producer: TMA bulk copies of raw x rows (4-deep ring, one 12 KiB copy per tile) ->
-//              hi/lo split -> 128B-swizzled K-major smem tiles
-//   warp  12   TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
+// Warp roles (672 threads, one persistent CTA per SM):
+//   warps 0-15  epilogue: tcgen05.ld row r -> relu -> dot with W2 (smem broadcast, packed FFMA2)
+//               -> global; four warps per TMEM lane quarter, each taking every fourth 32-column
+//               chunk of the hidden units (partial sums meet in shared memory).  The epilogue is
+//               latency- and FMA-pipe-bound, hence four warps per SM sub-partition
+//   warps 16-19 producer: TMA bulk copies of raw x rows (4-deep ring, one 12 KiB copy per tile) ->
+//               hi/lo split -> 128B-swizzled K-major smem tiles
+//   warp  20    TMEM allocator + UMMA issuer (warp-uniform schedule, one elected lane issues)
 // Pipelines: smem stage full/empty mbarriers (producer <-> UMMA, freed by tcgen05.commit) and
 // TMEM stage full/empty mbarriers (UMMA <-> epilogue).
 #include <cstdlib>
@@ -34,7 +35,7 @@ constexpr int kTileM = 128;
 constexpr int kKPad = 32;     // floats per operand row = 128 bytes
 constexpr int kStages = 2;    // x tile stages in shared memory
 constexpr int kAccCols = 256; // TMEM columns per accumulator stage
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 21 * 32;
 constexpr int kTileBytes = kTileM * kKPad * 4;  // 16 KiB
 constexpr int kRawStages = 4;                   // bulk-copy ring depth
 constexpr int kRawStageBytes = kTileM * 28 * 4; // 14 KiB: 128 rows x O <= 28 floats
@@ -69,11 +70,11 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
     uint8_t* x_lo = x_hi + kStages * kTileBytes;
     uint8_t* raw = x_lo + kStages * kTileBytes;             // kRawStages x 14 KiB
     float* w2s = reinterpret_cast<float*>(raw + kRawStages * kRawStageBytes);  // [H][NP]
-    float* part = w2s + 256 * NP;                           // [2][128 rows][NP] partial sums of half 1
-    Barriers* bars = reinterpret_cast<Barriers*>(part + 2 * kTileM * NP);
+    float* part = w2s + 256 * NP;                           // [2][3][128 rows][NP] partial sums of column groups 1-3
+    Barriers* bars = reinterpret_cast<Barriers*>(part + 2 * 3 * kTileM * NP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 12);
+    const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 20);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();
     if (a.trace && blockIdx.x == 0)
@@ -92,7 +93,7 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
         w2s[idx] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
     }
     tc::fence_proxy_async();
-    if (warp == 12) {
+    if (warp == 20) {
         tc::tmem_alloc(&bars->tmem_base, 512);
         if (lane == 0) {
             for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
@@ -102,7 +103,7 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             }
             for (int s = 0; s < 2; ++s) {
                 tc::mbar_init(&bars->acc_full[s], 1);        // tcgen05.commit
-                tc::mbar_init(&bars->acc_empty[s], 8 * 32);  // every epilogue thread arrives
+                tc::mbar_init(&bars->acc_empty[s], 16 * 32);  // every epilogue thread arrives
             }
             tc::mbar_fence_init();
         }
@@ -112,14 +113,17 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
     tc::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < 8) {
+    if (warp < 16) {
         // =============================== epilogue ===============================
-        const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
-        const int nch = H >> 5, nch0 = (nch + 1) >> 1;
-        const int cb_lo = half == 0 ? 0 : 32 * nch0, cb_hi = half == 0 ? 32 * nch0 : H;
-        float b2r[NP];
-#pragma unroll
-        for (int n = 0; n < NP; ++n) b2r[n] = (half == 0 && n < a.N2) ? __ldg(b2 + n) : 0.f;
+        const int q = warp & 3, grp = warp >> 2;  // TMEM lane quarter, column group
+        const int nch = H >> 5;                   // 32-column chunks; group g takes chunks g, g + 4
+        float2 b2p[NP == 4 ? 2 : 1];
+        if constexpr (NP == 4) {
+            b2p[0] = make_float2(grp == 0 && 0 < a.N2 ? __ldg(b2 + 0) : 0.f, grp == 0 && 1 < a.N2 ? __ldg(b2 + 1) : 0.f);
+            b2p[1] = make_float2(grp == 0 && 2 < a.N2 ? __ldg(b2 + 2) : 0.f, grp == 0 && 3 < a.N2 ? __ldg(b2 + 3) : 0.f);
+        } else {
+            b2p[0] = make_float2(grp == 0 ? __ldg(b2) : 0.f, 0.f);
+        }
         int it = 0;
         for (int tile = cta; tile < a.num_tiles; tile += ncta, ++it) {
             const int as = it & 1, aph = (it >> 1) & 1;
@@ -128,71 +132,81 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             tc::tc_fence_after();
             TRACE(it, 1)
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
-            float acc0[NP], acc1[NP];
+            // NP == 4: acc[0] = outputs (0,1), acc[1] = outputs (2,3); NP == 1: acc[0] = (even, odd
+            // column) partial sums of the single output
+            float2 acc[NP == 4 ? 2 : 1];
 #pragma unroll
-            for (int n = 0; n < NP; ++n) acc0[n] = b2r[n], acc1[n] = 0.f;
-            for (int cb = cb_lo; cb < cb_hi; cb += 64) {  // up to two 32-column loads in flight
-                uint32_t raw0[32], raw1[32];
-                const bool two = cb + 32 < cb_hi;
-                tc::tmem_ld32_nowait(taddr + cb, raw0);
-                if (two) tc::tmem_ld32_nowait(taddr + cb + 32, raw1);
-                tc::tmem_wait_ld();
-#pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    if (hb == 1 && !two) break;
-                    const int c0 = cb + 32 * hb;
+            for (int k = 0; k < (NP == 4 ? 2 : 1); ++k) acc[k] = b2p[k];
+            // chunk by chunk (32 live accumulator registers at a time: 672 threads leave 80 each)
+#pragma unroll 1
+            for (int hb = 0; hb < 2; ++hb) {
+                const int ch = grp + 4 * hb;
+                const bool last = ch + 4 >= nch || hb == 1;
+                float raw[32];
+                if (ch < nch) tc::tmem_ld32(taddr + 32 * ch, raw);  // waits for the data
+                if (last) {  // all of this thread's TMEM reads are complete: release the stage
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&bars->acc_empty[as]);
+                }
+                if (ch < nch) {
+                    const int c0 = 32 * ch;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float h0 = fmaxf(__uint_as_float(hb ? raw1[i] : raw0[i]), 0.f);
-                        const float h1 = fmaxf(__uint_as_float(hb ? raw1[i + 1] : raw0[i + 1]), 0.f);
+                        const float h0 = fmaxf(raw[i], 0.f);
+                        const float h1 = fmaxf(raw[i + 1], 0.f);
                         if constexpr (NP == 4) {
                             const float4 wa = *reinterpret_cast<const float4*>(w2s + (c0 + i) * 4);
                             const float4 wb = *reinterpret_cast<const float4*>(w2s + (c0 + i + 1) * 4);
-                            acc0[0] = fmaf(h0, wa.x, acc0[0]), acc0[1] = fmaf(h0, wa.y, acc0[1]);
-                            acc0[2] = fmaf(h0, wa.z, acc0[2]), acc0[3] = fmaf(h0, wa.w, acc0[3]);
-                            acc1[0] = fmaf(h1, wb.x, acc1[0]), acc1[1] = fmaf(h1, wb.y, acc1[1]);
-                            acc1[2] = fmaf(h1, wb.z, acc1[2]), acc1[3] = fmaf(h1, wb.w, acc1[3]);
+                            const float2 h0p = make_float2(h0, h0), h1p = make_float2(h1, h1);
+                            acc[0] = tc::ffma2(h0p, make_float2(wa.x, wa.y), acc[0]);
+                            acc[1] = tc::ffma2(h0p, make_float2(wa.z, wa.w), acc[1]);
+                            acc[0] = tc::ffma2(h1p, make_float2(wb.x, wb.y), acc[0]);
+                            acc[1] = tc::ffma2(h1p, make_float2(wb.z, wb.w), acc[1]);
                         } else {
                             const float2 w = *reinterpret_cast<const float2*>(w2s + c0 + i);
-                            acc0[0] = fmaf(h0, w.x, acc0[0]);
-                            acc1[0] = fmaf(h1, w.y, acc1[0]);
+                            acc[0] = tc::ffma2(make_float2(h0, h1), w, acc[0]);
                         }
                     }
                 }
+                if (last) break;
             }
-            // all of this thread's TMEM reads are complete (wait::ld): release the stage
-            tc::tc_fence_before();
-            tc::mbar_arrive(&bars->acc_empty[as]);
             TRACE(it, 2)
             const int rl = 32 * q + lane;  // row of the tile
-            float* pbuf = part + ((it & 1) * kTileM + rl) * NP;
-            if (half == 1) {
-#pragma unroll
-                for (int n = 0; n < NP; ++n) pbuf[n] = acc0[n] + acc1[n];
+            float* pbuf = part + (it & 1) * 3 * kTileM * NP;
+            if (grp > 0) {
+                float* pb = pbuf + ((grp - 1) * kTileM + rl) * NP;
+                if constexpr (NP == 4) *reinterpret_cast<float4*>(pb) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                else pb[0] = acc[0].x + acc[0].y;
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");  // the two column halves meet
+            asm volatile("bar.sync 2, 512;" ::: "memory");  // the four column groups meet
             const int row = tile * kTileM + rl;
-            if (half == 0 && row < a.M) {
-                if (NP == 4 && a.N2 == 4) {
-                    const float4 o = *reinterpret_cast<const float4*>(pbuf);
-                    *reinterpret_cast<float4*>(a.out + (size_t)row * 4) =
-                        make_float4(acc0[0] + acc1[0] + o.x, acc0[1] + acc1[1] + o.y,
-                                    acc0[2] + acc1[2] + o.z, acc0[3] + acc1[3] + o.w);
-                } else {
+            if (grp == 0 && row < a.M) {
+                if constexpr (NP == 4) {
+                    const float4 p1 = *reinterpret_cast<const float4*>(pbuf + (0 * kTileM + rl) * 4);
+                    const float4 p2 = *reinterpret_cast<const float4*>(pbuf + (1 * kTileM + rl) * 4);
+                    const float4 p3 = *reinterpret_cast<const float4*>(pbuf + (2 * kTileM + rl) * 4);
+                    const float o[4] = {((acc[0].x + p1.x) + p2.x) + p3.x, ((acc[0].y + p1.y) + p2.y) + p3.y,
+                                        ((acc[1].x + p1.z) + p2.z) + p3.z, ((acc[1].y + p1.w) + p2.w) + p3.w};
+                    if (a.N2 == 4) {
+                        *reinterpret_cast<float4*>(a.out + (size_t)row * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
 #pragma unroll
-                    for (int n = 0; n < NP; ++n)
-                        if (n < a.N2) a.out[(size_t)row * a.N2 + n] = acc0[n] + acc1[n] + pbuf[n];
+                        for (int n = 0; n < 4; ++n)
+                            if (n < a.N2) a.out[(size_t)row * a.N2 + n] = o[n];
+                    }
+                } else {
+                    a.out[row] = (((acc[0].x + acc[0].y) + pbuf[rl]) + pbuf[kTileM + rl]) + pbuf[2 * kTileM + rl];
                 }
             }
         }
-    } else if (warp < 12) {
+    } else if (warp < 20) {
         // =============================== producer ===============================
-        const int r = 32 * (warp - 8) + lane;  // row of the tile this thread converts
+        const int r = 32 * (warp - 16) + lane;  // row of the tile this thread converts
         const int n_my = (a.num_tiles - cta + ncta - 1) / ncta;
         auto tile_of = [&](int i) { return cta + i * ncta; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kTileM <= a.M; };
         auto issue_raw = [&](int i) {
-            if (warp == 8 && lane == 0 && is_full(i)) {
+            if (warp == 16 && lane == 0 && is_full(i)) {
                 const int rs = i % kRawStages;
                 const uint32_t bytes = kTileM * O * 4;
                 tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
@@ -267,13 +281,16 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             TRACE(it, 10)
             if (tc::elect_one()) {
                 const uint32_t d = tmem_base + as * kAccCols;
-                const uint64_t so = static_cast<uint64_t>((s * kTileBytes) >> 4);
-#pragma unroll 1
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint64_t ko = 2 * kk;  // 32 bytes per K = 8 step, in 16-byte units
-                    tc::umma_tf32(d, dx_hi + so + ko, dw_hi + ko, idesc, kk > 0);
-                    tc::umma_tf32(d, dx_lo + so + ko, dw_hi + ko, idesc, true);
-                    tc::umma_tf32(d, dx_hi + so + ko, dw_lo + ko, idesc, true);
+                const uint64_t xh = dx_hi + static_cast<uint64_t>((s * kTileBytes) >> 4);
+                const uint64_t xl = dx_lo + static_cast<uint64_t>((s * kTileBytes) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {  // unrolled with uniform guards: constant descriptor offsets
+                    if (kk < ksteps) {
+                        const uint64_t ko = 2 * kk;  // 32 bytes per K = 8 step, in 16-byte units
+                        tc::umma_tf32(d, xh + ko, dw_hi + ko, idesc, kk > 0);
+                        tc::umma_tf32(d, xl + ko, dw_hi + ko, idesc, true);
+                        tc::umma_tf32(d, xh + ko, dw_lo + ko, idesc, true);
+                    }
                 }
                 tc::umma_commit(&bars->empty[s]);      // smem stage reusable once the UMMAs retire
                 tc::umma_commit(&bars->acc_full[as]);  // accumulator ready for the epilogue
@@ -285,7 +302,7 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == 20) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
@@ -315,7 +332,7 @@ mlp_fwd_tc_pair_kernel(const __grid_constant__ FwdTcArgs a_pi, const __grid_cons
 }
 
 constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + 2 * 256 * 128 + 2 * kStages * kTileBytes +
-                              kRawStages * kRawStageBytes + (256 + 2 * kTileM) * 4 * sizeof(float) + sizeof(Barriers);
+                              kRawStages * kRawStageBytes + (256 + 2 * 3 * kTileM) * 4 * sizeof(float) + sizeof(Barriers);
 
 }  // namespace
 
