@@ -10,13 +10,18 @@ import torch  # noqa: E402
 
 from torched_impala_b200 import _cabi, ops, synth  # noqa: E402
 
-M, O, H, N2 = 86016, 24, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 1
+PAIR = len(sys.argv) > 1 and sys.argv[1] == "pair"  # c4 pair launch: CTA 0 is a policy CTA
+M, O, H, N2 = 86016, 24, 256, 4 if PAIR else (int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 rng = np.random.default_rng(0)
 p = synth.init_params(0, O, N2, H)["policy"]
 x = torch.from_numpy(rng.standard_normal((M, O), dtype=np.float32)).cuda()
 pp = ops.pack_params(p)
+pv = ops.pack_params(synth.init_params(1, O, 1, H)["policy"])
 for _ in range(3):
-    ops.mlp_forward(x, pp, O, H, N2)
+    if PAIR:
+        ops.mlp_forward_pair(x, pp, pv, 81920, M, O, H, H, 4)
+    else:
+        ops.mlp_forward(x, pp, O, H, N2)
 torch.cuda.synchronize()
 fn = _cabi.lib().impala_debug_read_trace_fwd
 fn.restype = C.c_int
