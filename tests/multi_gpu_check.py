@@ -54,7 +54,7 @@ def main():
             ref.step(u % 2)
             want = ref.read_scalars()
             for k in ("value_fn_loss", "policy_loss", "policy_entropy", "total_loss", "batch_mean_reward"):
-                assert abs(scal[u][k] - want[k]) < 1e-5, (u, k, scal[u][k], want[k])
+                assert abs(scal[u][k] - want[k]) < 1e-5 * max(1.0, abs(want[k])), (u, k, scal[u][k], want[k])
         d = (mine - ref.params).abs().max().item()
         assert d < 2e-5, d
         print(f"MULTI_GPU_OK world={world} max|dparam|={d:.2e} loss={scal[-1]['total_loss']:.6f}")
