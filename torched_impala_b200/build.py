@@ -35,7 +35,7 @@ def _units():
     units = [("mlp", "mlp.cu", []), ("vtrace_loss", "vtrace_loss.cu", []),
              ("optim", "optim.cu", []), ("abi", "abi.cu", []),
              ("mlp_fwd_tc", "mlp_fwd_tc.cu", []), ("mlp_bwd_tc", "mlp_bwd_tc.cu", []),
-             ("loss_terms", "loss_terms.cu", []), ("tmem_diag", "tmem_diag.cu", [])]
+             ("loss_terms", "loss_terms.cu", [])]
     for op in MLP_WIDTHS:
         for bwd in (0, 1):
             units.append((f"mlp_inst_op{op}_{'bwd' if bwd else 'fwd'}", "mlp_inst.cu",
