@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Own arm (default): one process per GPU (torchrun for N > 1), global batch B=4096 sharded
-B/N per rank ("scaling": "strong"), one NCCL all-reduce of [gradient | loss scalars] per step.
+B/N per rank ("scaling": "strong"), one all-reduce of [gradient | loss scalars] per step (done by the
+optimizer kernel over NVLink peer memory; NCCL with IMPALA_ALLREDUCE=nccl).
   value  : learner steps/s with the batch already resident in HBM; each of the K timed steps
            is bracketed by CUDA events on the launching stream, L2 flushed between steps
   e2e    : the same through the host-facing API - every step copies that step's inputs from
@@ -276,7 +277,9 @@ def kernel_breakdown(eng, flush, iters=20):
         for dst, src in zip((eng.params, eng.adam_m, eng.adam_v, eng.adam_step), keep):
             dst.copy_(src)
         # read grad f64 + params/m/v read+write f32
-        out["clip_adam"] = dict(us=statistics.median(ts), flops=None, bytes=(8.0 + 6 * 4.0) * eng.n_total)
+        # read grad f64 (from every rank when the kernel all-reduces over peer memory) + params/m/v rw
+        out["allreduce+clip_adam" if eng.peer else "clip_adam"] = dict(
+            us=statistics.median(ts), flops=None, bytes=(8.0 * eng.world + 6 * 4.0) * eng.n_total)
     eng.synchronize()
     return out
 
@@ -426,7 +429,8 @@ def run_own_arm(args):
             ent.update(bound="hbm", achieved=round(ach, 1), peak=pk["hbm_gbs"], unit="GB/s",
                        frac=round(ach / pk["hbm_gbs"], 4))
         kernels[name] = ent
-    in_step = ("mlp_forward_pair(policy+value_fn)", "vtrace_loss", "mlp_backward_pair(policy+value_fn)", "clip_adam")
+    in_step = ("mlp_forward_pair(policy+value_fn)", "vtrace_loss", "mlp_backward_pair(policy+value_fn)",
+               "allreduce+clip_adam" if eng.peer else "clip_adam")
     for n in kernels:
         kernels[n]["in_step"] = n in in_step
     dom = max(in_step, key=lambda n: kernels[n]["us"])
@@ -460,7 +464,8 @@ def run_own_arm(args):
         warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True, scaling="strong",
         vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=WORKLOAD_NAME, **w, global_batch=w["B"], per_gpu_batch=Bl,
-                    parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step)"
+                    parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step, "
+                                f"{'in the optimizer kernel over NVLink peer memory' if eng.peer else 'NCCL'})"
                     if world > 1 else "single GPU",
                     l2="flushed between timed steps (256 MiB memset on the launching stream)",
                     cuda_graph=not args.no_graph, timing="sum of per-step CUDA-event intervals, max over ranks"),

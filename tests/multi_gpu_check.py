@@ -57,7 +57,8 @@ def main():
                 assert abs(scal[u][k] - want[k]) < 1e-5 * max(1.0, abs(want[k])), (u, k, scal[u][k], want[k])
         d = (mine - ref.params).abs().max().item()
         assert d < 2e-5, d
-        print(f"MULTI_GPU_OK world={world} max|dparam|={d:.2e} loss={scal[-1]['total_loss']:.6f}")
+        print(f"MULTI_GPU_OK world={world} allreduce={'peer' if eng.peer else 'nccl'} max|dparam|={d:.2e} "
+              f"loss={scal[-1]['total_loss']:.6f}")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,4 +1,5 @@
-"""GPU (>= 2 devices): data-parallel learner over NCCL equals the single-GPU full-batch learner."""
+"""GPU (>= 2 devices): the data-parallel learner equals the single-GPU full-batch learner, with the
+gradient all-reduce done by the optimizer kernel over NVLink peer memory (default) and by NCCL."""
 import os
 import socket
 import subprocess
@@ -10,7 +11,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_two_rank_nccl_matches_single_gpu():
+@pytest.mark.parametrize("allreduce", ["peer", "nccl"])
+def test_two_rank_learner_matches_single_gpu(allreduce):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     with socket.socket() as s:
@@ -19,6 +21,8 @@ def test_two_rank_nccl_matches_single_gpu():
     script = os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), script],
-                         capture_output=True, text=True, timeout=240)
+                         capture_output=True, text=True, timeout=240,
+                         env=dict(os.environ, IMPALA_ALLREDUCE=allreduce))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout
+    assert f"allreduce={allreduce}" in res.stdout  # the requested path is the one that ran

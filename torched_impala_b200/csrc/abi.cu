@@ -1,4 +1,6 @@
 // Layout helpers and ingest: the parts of the C ABI that launch no kernel of their own.
+#include <string.h>
+
 #include "common.cuh"
 
 extern "C" int impala_abi_version(void) { return 1; }
@@ -38,5 +40,35 @@ extern "C" int impala_ingest(void* dev_slab, const void* host_slab, int64_t byte
     if (!dev_slab || !host_slab || bytes < 0) return IMPALA_ERR_BAD_ARG;
     cudaError_t e = cudaMemcpyAsync(dev_slab, host_slab, (size_t)bytes, cudaMemcpyHostToDevice,
                                     (cudaStream_t)stream);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
+// ---- node-local peer buffers (CUDA IPC) for impala_allreduce_clip_adam
+extern "C" int impala_peer_alloc(int64_t bytes, void** dev_ptr, void* handle64) {
+    if (bytes < 1 || !dev_ptr || !handle64) return IMPALA_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaError_t e = cudaMalloc(dev_ptr, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    if ((e = cudaMemset(*dev_ptr, 0, (size_t)bytes)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
+    e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *dev_ptr);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
+extern "C" int impala_peer_open(const void* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return IMPALA_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
+extern "C" int impala_peer_close(void* dev_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
+extern "C" int impala_peer_free(void* dev_ptr) {
+    cudaError_t e = cudaFree(dev_ptr);
     return e == cudaSuccess ? IMPALA_OK : (int)e;
 }

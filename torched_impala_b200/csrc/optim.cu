@@ -116,6 +116,179 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Data-parallel learners: one-shot all-reduce over NVLink peer memory fused with clip + Adam.
+//
+// Every rank leaves its float64 [gradient | extra scalars] contribution in a buffer that the other
+// ranks of the node have mapped (CUDA IPC).  Instead of an NCCL all-reduce between the backward
+// and the optimizer, the optimizer kernel of each rank
+//   1. posts "my contribution for step s is complete" into every peer's flag block,
+//   2. waits until all ranks' flags for step s have arrived in its own block,
+//   3. reads element i from all ranks (peer loads over NVLink / NVSwitch) and adds them in rank
+//      order - every rank forms bit-identical sums, so the replicas cannot drift,
+//   4. posts "I have read your buffer" to every peer, runs the clip norms and Adam on the sum, and
+//   5. leaves only when all peers have acknowledged reading ITS buffer (so the next backward may
+//      overwrite it whatever the caller's buffering scheme).
+// Flags are monotonically increasing step numbers (int64, never reset); spins are bounded by a
+// clock timeout that traps (a lost rank becomes a launch failure on the others, not a hang).
+// Flag block of a rank: int64[2 * world] = ready[world] | ack[world], indexed by the WRITING rank.
+struct PeerArgs {
+    const double* const* contrib;  // device array [world]: every rank's [n_total + n_extra] doubles
+    long long* const* flags;       // device array [world]: every rank's flag block
+    long long* seq;                // this rank's step counter (device, 1 word)
+    int rank, world, n_extra;
+};
+
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {  // not served from a local cache
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// lane r of the calling warp polls entry r of the block (all ranks in parallel), then the warp meets
+__device__ __forceinline__ void wait_flags(const long long* block, int n, long long seq, int lane) {
+    if (lane < n) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(block + lane) < seq)
+            if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a peer is gone
+    }
+    __syncwarp();
+}
+
+__global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(kAdamThreads)
+allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced, PeerArgs peer,
+                           float* __restrict__ m, float* __restrict__ v, int64_t* __restrict__ state,
+                           int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
+                           float beta2, float eps, double* __restrict__ norms_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_warp[2][kAdamThreads / 32];
+    __shared__ double s_cta[2];
+    __shared__ float s_coef[2];
+    __shared__ float s_bias[2];
+    __shared__ double s_pow[2];
+    __shared__ long long s_seq;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int crank = (int)cluster.block_rank();
+    const int64_t first = (int64_t)crank * kAdamThreads + tid;
+    const int64_t stride = (int64_t)kAdamCluster * kAdamThreads;
+    long long* my_flags = peer.flags[peer.rank];
+
+    // 1. + 2.: post "ready" to everyone (one CTA, one lane per peer), then every CTA waits for all
+    // ranks' flags.  This rank's contribution was written by earlier kernels of the stream, i.e. it
+    // is already performed in its L2 (where peer reads are served); one system fence orders the
+    // flag stores behind it.
+    if (warp == 0) {
+        const long long seq = *peer.seq + 1;
+        if (lane == 0) s_seq = seq;
+        if (crank == 0) {
+            __threadfence_system();
+            if (lane < peer.world) st_relaxed_sys(peer.flags[lane] + peer.rank, seq);
+        }
+        wait_flags(my_flags, peer.world, seq, lane);
+    }
+    if (tid == 64) {  // bias corrections from the running powers (nobody writes state before the end)
+        const double p1 = state[0] == 0 ? 1.0 : __longlong_as_double(state[1]);
+        const double p2 = state[0] == 0 ? 1.0 : __longlong_as_double(state[2]);
+        s_pow[0] = p1 * (double)beta1, s_pow[1] = p2 * (double)beta2;
+        s_bias[0] = (float)((double)lr / (1.0 - s_pow[0]));
+        s_bias[1] = (float)(1.0 / sqrt(1.0 - s_pow[1]));
+    }
+    __syncthreads();
+
+    // 3. rank-ordered sums of this thread's entries (all loads of an entry are independent)
+    constexpr int kKeep = 2, kMaxWorld = 8;  // one NVLink node
+    auto gather = [&](int64_t i) {
+        double c[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < peer.world) c[r] = ld_peer_f64(peer.contrib[r] + i);
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < peer.world) s += c[r];
+        return s;
+    };
+    double gk[kKeep];
+    float pk[kKeep], mk[kKeep], vk[kKeep];
+    double ss0 = 0.0, ss1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int64_t i = first + k * stride;
+        gk[k] = i < n_total ? gather(i) : 0.0;
+        pk[k] = i < n_total ? params[i] : 0.f;
+        mk[k] = i < n_total ? m[i] : 0.f;
+        vk[k] = i < n_total ? v[i] : 0.f;
+        if (i < n_total) reduced[i] = gk[k];
+        if (i < n_policy) ss0 += gk[k] * gk[k];
+        else ss1 += gk[k] * gk[k];
+    }
+    for (int64_t i = first + kKeep * stride; i < n_total; i += stride) {
+        const double g = gather(i);
+        reduced[i] = g;
+        if (i < n_policy) ss0 += g * g;
+        else ss1 += g * g;
+    }
+    if (crank == 0 && tid < peer.n_extra) reduced[n_total + tid] = gather(n_total + tid);  // logged scalars
+    ss0 = warp_sum_f64(ss0);
+    ss1 = warp_sum_f64(ss1);
+    if (lane == 0) s_warp[0][warp] = ss0, s_warp[1][warp] = ss1;
+    __syncthreads();
+    if (tid < 2) {
+        double s = 0.0;
+        for (int i = 0; i < kAdamThreads / 32; ++i) s += s_warp[tid][i];
+        s_cta[tid] = s;
+    }
+    cluster.sync();  // all 8 partial pairs are in place; every CTA has finished its peer reads
+    // 4. acknowledge: the peers' buffers have been consumed by this rank (their values are in
+    // registers / already summed, so a relaxed store cannot overtake the loads)
+    if (crank == 0 && tid < peer.world) st_relaxed_sys(peer.flags[tid] + peer.world + peer.rank, s_seq);
+    if (tid < 2) {
+        double s = 0.0;
+        for (int r = 0; r < kAdamCluster; ++r) s += *cluster.map_shared_rank(&s_cta[tid], r);
+        const double norm = sqrt(s);
+        s_coef[tid] = (float)fmin(1.0, (double)max_norm / (norm + 1e-6));
+        if (norms_out && crank == 0) norms_out[tid] = norm;
+    }
+    __syncthreads();
+    const float b1 = beta1, b2 = beta2, step_size = s_bias[0], inv_bc2_sqrt = s_bias[1];
+    const float c0 = s_coef[0], c1 = s_coef[1];
+    auto update = [&](int64_t i, float g, float p, float mi, float vi) {
+        g *= (i < n_policy ? c0 : c1);
+        mi = fmaf(b1, mi, (1.f - b1) * g);
+        vi = fmaf(b2, vi, (1.f - b2) * g * g);
+        const float denom = fmaf(sqrtf(vi), inv_bc2_sqrt, eps);
+        params[i] = p - step_size * mi / denom;
+        m[i] = mi;
+        v[i] = vi;
+    };
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int64_t i = first + k * stride;
+        if (i < n_total) update(i, (float)gk[k], pk[k], mk[k], vk[k]);
+    }
+    for (int64_t i = first + kKeep * stride; i < n_total; i += stride)
+        update(i, (float)reduced[i], params[i], m[i], v[i]);
+    cluster.sync();  // peers finished reading this CTA's shared memory; every CTA has read state
+    if (crank == 0 && tid == 64) {
+        state[0] += 1;
+        state[1] = __double_as_longlong(s_pow[0]);
+        state[2] = __double_as_longlong(s_pow[1]);
+    }
+    // 5. this rank's buffer may be overwritten once every peer has read it
+    if (crank == 0 && warp == 0) {
+        wait_flags(my_flags + peer.world, peer.world, s_seq, lane);
+        if (lane == 0) *peer.seq = s_seq;
+    }
+}
+
 }  // namespace
 
 extern "C" int impala_clip_adam(float* params, const double* grad, float* m, float* v,
@@ -126,5 +299,21 @@ extern "C" int impala_clip_adam(float* params, const double* grad, float* m, flo
     if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
     clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
         params, grad, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
+    return impala_launch_status();
+}
+
+extern "C" int impala_allreduce_clip_adam(float* params, double* reduced, const double* const* peer_contrib,
+                                          long long* const* peer_flags, long long* seq, int rank, int world,
+                                          int n_extra, float* m, float* v, int64_t* state, int64_t n_policy,
+                                          int64_t n_total, float max_norm, float lr, float beta1, float beta2,
+                                          float eps, double* norms_out, void* stream) {
+    if (!params || !reduced || !peer_contrib || !peer_flags || !seq || !m || !v || !state)
+        return IMPALA_ERR_BAD_ARG;
+    if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || n_extra < 0 || n_extra > kAdamThreads)
+        return IMPALA_ERR_BAD_ARG;
+    PeerArgs peer{peer_contrib, peer_flags, seq, rank, world, n_extra};
+    allreduce_clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
+        params, reduced, peer, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
     return impala_launch_status();
 }

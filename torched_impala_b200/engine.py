@@ -127,8 +127,64 @@ class LearnerEngine:
         self._graph_opt = None
         self._main_launches = 0
         self.steps_done = 0
+        self.peer = None
+        if self.world > 1:
+            self._setup_peer_allreduce()
 
     # ------------------------------------------------------------------ parameters
+    # ------------------------------------------------------------------------ multi-GPU plumbing
+    def _setup_peer_allreduce(self) -> None:
+        """Map every rank's contribution buffer and flag block (CUDA IPC over NVLink) for
+        impala_allreduce_clip_adam.  IMPALA_ALLREDUCE=nccl - or a failed mapping on ANY rank - keeps
+        the torch.distributed all-reduce between the backward and the optimizer instead."""
+        import os
+        import warnings
+
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(self.pg), self.world
+        ok, err, mine = os.environ.get("IMPALA_ALLREDUCE", "peer") != "nccl" and world <= 8, "", {}
+        n_doubles, lib = self.n_total + 8, self.lib
+        if ok:
+            try:
+                for name, nbytes in (("contrib", 8 * n_doubles), ("flags", 8 * 2 * world)):
+                    ptr, handle = C.c_void_p(), (C.c_char * 64)()
+                    _cabi.check(lib.impala_peer_alloc(nbytes, C.byref(ptr), handle), "impala_peer_alloc")
+                    mine[name] = (ptr.value, bytes(handle.raw))
+            except Exception as e:  # noqa: BLE001 - reported below, all ranks fall back together
+                ok, err = False, repr(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, {k: v[1] for k, v in mine.items()} if ok else None, group=self.pg)
+        ok = ok and all(h is not None for h in handles)
+        ptrs = {"contrib": [], "flags": []}
+        opened = []
+        if ok:
+            try:
+                for r, h in enumerate(handles):
+                    for name in ("contrib", "flags"):
+                        if r == rank:
+                            ptrs[name].append(mine[name][0])
+                        else:
+                            ptr = C.c_void_p()
+                            _cabi.check(lib.impala_peer_open(h[name], C.byref(ptr)), f"impala_peer_open(rank {r})")
+                            opened.append(ptr.value)
+                            ptrs[name].append(ptr.value)
+            except Exception as e:  # noqa: BLE001
+                ok, err = False, repr(e)
+        agree = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(agree.item()) == 0:
+            if os.environ.get("IMPALA_ALLREDUCE", "peer") != "nccl" and rank == 0:
+                warnings.warn(f"peer-memory all-reduce unavailable ({err or 'a rank could not map its peers'}); "
+                              "using the NCCL all-reduce between backward and optimizer")
+            return
+        i64 = dict(dtype=torch.int64, device=self.dev)
+        self.peer = dict(contrib=mine["contrib"][0], flags=mine["flags"][0], opened=opened,
+                         contrib_ptrs=torch.tensor(ptrs["contrib"], **i64), flag_ptrs=torch.tensor(ptrs["flags"], **i64),
+                         seq=torch.zeros(1, **i64), rank=rank)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.pg)
+
     def _ws_bytes(self, M, O, H, N2):
         n = self.lib.impala_mlp_backward_workspace(M, O, H, N2)
         if n < 0:
@@ -226,9 +282,12 @@ class LearnerEngine:
         T, B, O, A = self.T, self.B, self.O, self.A
         p_pi = C.c_void_p(self.params.data_ptr())
         p_vf = C.c_void_p(self.params.data_ptr() + 4 * self.n_pi)
-        g_pi = C.c_void_p(self.comm.data_ptr())
-        g_vf = C.c_void_p(self.comm.data_ptr() + 8 * self.n_pi)
-        scal = C.c_void_p(self.comm.data_ptr() + 8 * self.n_total)
+        # this rank's [gradient | scalars]: the peer-mapped contribution buffer when the optimizer
+        # kernel does the all-reduce itself, else `comm` (reduced in place by NCCL, or final at N=1)
+        gbase = self.peer["contrib"] if self.peer else self.comm.data_ptr()
+        g_pi = C.c_void_p(gbase)
+        g_vf = C.c_void_p(gbase + 8 * self.n_pi)
+        scal = C.c_void_p(gbase + 8 * self.n_total)
         obs = _ptr(d["obs"])
         _cabi.check(lib.impala_mlp_forward_pair(obs, p_pi, p_vf, _ptr(self.logits), _ptr(self.values),
                                                 self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
@@ -265,6 +324,14 @@ class LearnerEngine:
 
     def _enqueue_opt(self) -> int:
         hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.peer:
+            pr = self.peer
+            _cabi.check(self.lib.impala_allreduce_clip_adam(
+                _ptr(self.params), _ptr(self.comm), _ptr(pr["contrib_ptrs"]), _ptr(pr["flag_ptrs"]),
+                _ptr(pr["seq"]), pr["rank"], self.world, 4, _ptr(self.adam_m), _ptr(self.adam_v),
+                _ptr(self.adam_step), self.n_pi, self.n_total, float(hp.max_norm), float(0.95 * hp.lr),
+                0.9, 0.999, 1e-8, _ptr(self.norms), st), "impala_allreduce_clip_adam")
+            return 1
         _cabi.check(self.lib.impala_clip_adam(
             _ptr(self.params), _ptr(self.comm), _ptr(self.adam_m), _ptr(self.adam_v),
             _ptr(self.adam_step), self.n_pi, self.n_total, float(hp.max_norm),
@@ -277,14 +344,18 @@ class LearnerEngine:
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, stream=self.stream):
                 self._main_launches = self._enqueue_main(slot)
-                if self.world == 1:  # no collective in between: the optimizer joins the same graph
+                if self._one_graph():  # no library collective in between: the optimizer joins the graph
                     self._enqueue_opt()
             self._graph_main[slot] = g1
-            if self.world > 1 and self._graph_opt is None:
+            if not self._one_graph() and self._graph_opt is None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, stream=self.stream):
                     self._enqueue_opt()
                 self._graph_opt = g2
+
+    def _one_graph(self) -> bool:
+        """Single GPU, or the optimizer kernel all-reduces over peer memory itself."""
+        return self.world == 1 or self.peer is not None
 
     def step(self, slot: int = 0) -> None:
         """One learner update on the batch in device slab `slot` (async on `self.stream`)."""
@@ -295,13 +366,13 @@ class LearnerEngine:
                     self._capture(slot)
                 self._graph_main[slot].replay()
                 n = self._main_launches
-                fused_opt = self.world == 1
+                fused_opt = self._one_graph()
             else:
                 n = self._enqueue_main(slot)  # first step eager: fills the launch-config caches
                 fused_opt = False
             self.slab_free[slot].record(self.stream)
             self._slab_used[slot] = True
-            if self.world > 1:
+            if self.world > 1 and not self.peer:
                 import torch.distributed as dist
 
                 dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)
