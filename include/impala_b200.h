@@ -152,23 +152,25 @@ int impala_peer_close(void* dev_ptr);
 int impala_peer_free(void* dev_ptr);
 
 /* Data-parallel learners on one NVLink node: the gradient all-reduce, the two clip norms and Adam
- * in ONE launch per rank, no collective library call.  Every rank's float64 contribution
- * [gradient (n_total) | n_extra logged scalars] lives in a buffer the other ranks have mapped
- * (CUDA IPC); peer_contrib[r] / peer_flags[r] are THIS process's device pointers to rank r's
- * buffer and flag block (int64[2 * world], zero-filled once; own entries included), both arrays in
- * device memory.  The kernel posts "ready", waits for all ranks, adds the world contributions
+ * in ONE launch per rank, no collective library call.  Every rank keeps TWO float64 contribution
+ * buffers [gradient (n_total) | n_extra logged scalars | pad], buf_stride doubles apart, in memory
+ * the other ranks have mapped (CUDA IPC); the backward of the k-th call (k = 0, 1, ...) writes
+ * buffer (k + 1) & 1.  peer_contrib[r] / peer_flags[r] are THIS process's device pointers to rank
+ * r's buffers and flag block (int64[world], zero-filled once; own entries included), both arrays
+ * in device memory.  The kernel posts "ready", waits for all ranks, adds the world contributions
  * of each entry in rank order (bit-identical sums on every rank), writes them to `reduced`
- * ([n_total + n_extra], local), acknowledges, applies impala_clip_adam's update, and returns only
- * after every peer has read this rank's buffer - the caller may overwrite it right after.  `seq`
- * is a device int64 (zero-filled once) that counts the calls; every rank must make the same
- * sequence of calls.  A rank that never arrives turns into a launch failure (trap after ~4 s) on
- * the others.  Replaces the DistributedDataParallel-style all-reduce a multi-GPU port of
- * learner.py:175-183 would place between loss.backward() and optimizer.step(). */
+ * ([n_total + n_extra], local) and applies impala_clip_adam's update.  The parity buffers replace
+ * a second handshake: a buffer is rewritten two calls later, after the ready flags of the call
+ * in between proved that every peer has finished reading it.  `seq` is a device int64 (zero-filled
+ * once) that counts the calls; every rank must make the same sequence of calls.  A rank that
+ * never arrives turns into a launch failure (trap after ~4 s) on the others.  Replaces the
+ * DistributedDataParallel-style all-reduce a multi-GPU port of learner.py:175-183 would place
+ * between loss.backward() and optimizer.step(). */
 int impala_allreduce_clip_adam(float* params, double* reduced, const double* const* peer_contrib,
-                               long long* const* peer_flags, long long* seq, int rank, int world,
-                               int n_extra, float* m, float* v, int64_t* state, int64_t n_policy,
-                               int64_t n_total, float max_norm, float lr, float beta1, float beta2,
-                               float eps, double* norms_out, void* stream);
+                               int64_t buf_stride, long long* const* peer_flags, long long* seq,
+                               int rank, int world, int n_extra, float* m, float* v, int64_t* state,
+                               int64_t n_policy, int64_t n_total, float max_norm, float lr,
+                               float beta1, float beta2, float eps, double* norms_out, void* stream);
 
 /* Pieces of the reference's module-level loss helpers (learner.py:298-321) for callers that use
  * them individually instead of impala_vtrace_loss.  logits (M,A) f32 row-major, actions (M) i32.

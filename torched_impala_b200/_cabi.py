@@ -39,7 +39,8 @@ SIGNATURES = {
     "impala_peer_open": (_i, [_p, _p]),
     "impala_peer_close": (_i, [_p]),
     "impala_peer_free": (_i, [_p]),
-    "impala_allreduce_clip_adam": (_i, [_p] * 5 + [_i] * 3 + [_p] * 3 + [_i64, _i64] + [_f] * 5 + [_p, _p]),
+    "impala_allreduce_clip_adam": (_i, [_p] * 3 + [_i64] + [_p] * 2 + [_i] * 3 + [_p] * 3 + [_i64, _i64] + [_f] * 5
+                                   + [_p, _p]),
     "impala_vtrace": (_i, [_p] * 9 + [_i, _i, _i, _f, _f, _f, _i, _p]),
     "impala_vtrace_loss_workspace": (_i64, [_i, _i, _i]),
     "impala_vtrace_loss": (_i, [_p] * 13 + [_i64, _i, _i, _i] + [_f] * 7 + [_i, _p]),

@@ -127,14 +127,18 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
 //   2. waits until all ranks' flags for step s have arrived in its own block,
 //   3. reads element i from all ranks (peer loads over NVLink / NVSwitch) and adds them in rank
 //      order - every rank forms bit-identical sums, so the replicas cannot drift,
-//   4. posts "I have read your buffer" to every peer, runs the clip norms and Adam on the sum, and
-//   5. leaves only when all peers have acknowledged reading ITS buffer (so the next backward may
-//      overwrite it whatever the caller's buffering scheme).
+//   4. runs the clip norms and Adam on the sum.
+// The contribution buffers are double-buffered by step parity (buffer s & 1 for step s), which
+// makes a second "I have read your buffer" round trip unnecessary: a rank overwrites buffer s & 1
+// in the backward of step s + 2, i.e. after its optimizer kernel of step s + 1 saw every peer's
+// ready flag for s + 1 - and a peer posts that flag only after its kernel of step s (the one that
+// read the buffer) has finished.
 // Flags are monotonically increasing step numbers (int64, never reset); spins are bounded by a
 // clock timeout that traps (a lost rank becomes a launch failure on the others, not a hang).
-// Flag block of a rank: int64[2 * world] = ready[world] | ack[world], indexed by the WRITING rank.
+// Flag block of a rank: int64[world], entry r written by rank r.
 struct PeerArgs {
-    const double* const* contrib;  // device array [world]: every rank's [n_total + n_extra] doubles
+    const double* const* contrib;  // device array [world]: every rank's 2 x [n_total + n_pad] doubles
+    int64_t buf_stride;            // doubles between the two parity buffers
     long long* const* flags;       // device array [world]: every rank's flag block
     long long* seq;                // this rank's step counter (device, 1 word)
     int rank, world, n_extra;
@@ -205,11 +209,12 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
 
     // 3. rank-ordered sums of this thread's entries (all loads of an entry are independent)
     constexpr int kKeep = 2, kMaxWorld = 8;  // one NVLink node
+    const int64_t boff = (s_seq & 1) * peer.buf_stride;  // this step's parity buffer
     auto gather = [&](int64_t i) {
         double c[kMaxWorld];
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < peer.world) c[r] = ld_peer_f64(peer.contrib[r] + i);
+            if (r < peer.world) c[r] = ld_peer_f64(peer.contrib[r] + boff + i);
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
@@ -247,9 +252,6 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
         s_cta[tid] = s;
     }
     cluster.sync();  // all 8 partial pairs are in place; every CTA has finished its peer reads
-    // 4. acknowledge: the peers' buffers have been consumed by this rank (their values are in
-    // registers / already summed, so a relaxed store cannot overtake the loads)
-    if (crank == 0 && tid < peer.world) st_relaxed_sys(peer.flags[tid] + peer.world + peer.rank, s_seq);
     if (tid < 2) {
         double s = 0.0;
         for (int r = 0; r < kAdamCluster; ++r) s += *cluster.map_shared_rank(&s_cta[tid], r);
@@ -282,11 +284,7 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
         state[1] = __double_as_longlong(s_pow[0]);
         state[2] = __double_as_longlong(s_pow[1]);
     }
-    // 5. this rank's buffer may be overwritten once every peer has read it
-    if (crank == 0 && warp == 0) {
-        wait_flags(my_flags + peer.world, peer.world, s_seq, lane);
-        if (lane == 0) *peer.seq = s_seq;
-    }
+    if (crank == 0 && tid == 0) *peer.seq = s_seq;
 }
 
 }  // namespace
@@ -303,8 +301,8 @@ extern "C" int impala_clip_adam(float* params, const double* grad, float* m, flo
 }
 
 extern "C" int impala_allreduce_clip_adam(float* params, double* reduced, const double* const* peer_contrib,
-                                          long long* const* peer_flags, long long* seq, int rank, int world,
-                                          int n_extra, float* m, float* v, int64_t* state, int64_t n_policy,
+                                          int64_t buf_stride, long long* const* peer_flags, long long* seq,
+                                          int rank, int world, int n_extra, float* m, float* v, int64_t* state, int64_t n_policy,
                                           int64_t n_total, float max_norm, float lr, float beta1, float beta2,
                                           float eps, double* norms_out, void* stream) {
     if (!params || !reduced || !peer_contrib || !peer_flags || !seq || !m || !v || !state)
@@ -312,7 +310,8 @@ extern "C" int impala_allreduce_clip_adam(float* params, double* reduced, const 
     if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
     if (world < 1 || world > 8 || rank < 0 || rank >= world || n_extra < 0 || n_extra > kAdamThreads)
         return IMPALA_ERR_BAD_ARG;
-    PeerArgs peer{peer_contrib, peer_flags, seq, rank, world, n_extra};
+    if (buf_stride < n_total + n_extra) return IMPALA_ERR_BAD_ARG;
+    PeerArgs peer{peer_contrib, buf_stride, peer_flags, seq, rank, world, n_extra};
     allreduce_clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
         params, reduced, peer, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
     return impala_launch_status();

@@ -123,7 +123,7 @@ class LearnerEngine:
         self._scalar_events = [torch.cuda.Event() for _ in range(4)]
         self._ticket = 0
 
-        self._graph_main = [None] * slabs
+        self._graph_main = {}  # (slab slot, contribution-buffer parity) -> captured step
         self._graph_opt = None
         self._main_launches = 0
         self.steps_done = 0
@@ -146,8 +146,8 @@ class LearnerEngine:
         ok, err, mine = os.environ.get("IMPALA_ALLREDUCE", "peer") != "nccl" and world <= 8, "", {}
         n_doubles, lib = self.n_total + 8, self.lib
         if ok:
-            try:
-                for name, nbytes in (("contrib", 8 * n_doubles), ("flags", 8 * 2 * world)):
+            try:  # two parity buffers of [gradient | scalars | pad]; one ready flag per rank
+                for name, nbytes in (("contrib", 2 * 8 * n_doubles), ("flags", 8 * world)):
                     ptr, handle = C.c_void_p(), (C.c_char * 64)()
                     _cabi.check(lib.impala_peer_alloc(nbytes, C.byref(ptr), handle), "impala_peer_alloc")
                     mine[name] = (ptr.value, bytes(handle.raw))
@@ -181,7 +181,7 @@ class LearnerEngine:
         i64 = dict(dtype=torch.int64, device=self.dev)
         self.peer = dict(contrib=mine["contrib"][0], flags=mine["flags"][0], opened=opened,
                          contrib_ptrs=torch.tensor(ptrs["contrib"], **i64), flag_ptrs=torch.tensor(ptrs["flags"], **i64),
-                         seq=torch.zeros(1, **i64), rank=rank)
+                         seq=torch.zeros(1, **i64), rank=rank, stride=n_doubles, calls=0)
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=self.pg)
 
@@ -284,7 +284,9 @@ class LearnerEngine:
         p_vf = C.c_void_p(self.params.data_ptr() + 4 * self.n_pi)
         # this rank's [gradient | scalars]: the peer-mapped contribution buffer when the optimizer
         # kernel does the all-reduce itself, else `comm` (reduced in place by NCCL, or final at N=1)
-        gbase = self.peer["contrib"] if self.peer else self.comm.data_ptr()
+        # (parity buffer (k + 1) & 1 for the k-th optimizer call, see impala_allreduce_clip_adam)
+        gbase = (self.peer["contrib"] + 8 * self.peer["stride"] * ((self.peer["calls"] + 1) & 1) if self.peer
+                 else self.comm.data_ptr())
         g_pi = C.c_void_p(gbase)
         g_vf = C.c_void_p(gbase + 8 * self.n_pi)
         scal = C.c_void_p(gbase + 8 * self.n_total)
@@ -327,10 +329,12 @@ class LearnerEngine:
         if self.peer:
             pr = self.peer
             _cabi.check(self.lib.impala_allreduce_clip_adam(
-                _ptr(self.params), _ptr(self.comm), _ptr(pr["contrib_ptrs"]), _ptr(pr["flag_ptrs"]),
+                _ptr(self.params), _ptr(self.comm), _ptr(pr["contrib_ptrs"]), pr["stride"], _ptr(pr["flag_ptrs"]),
                 _ptr(pr["seq"]), pr["rank"], self.world, 4, _ptr(self.adam_m), _ptr(self.adam_v),
                 _ptr(self.adam_step), self.n_pi, self.n_total, float(hp.max_norm), float(0.95 * hp.lr),
                 0.9, 0.999, 1e-8, _ptr(self.norms), st), "impala_allreduce_clip_adam")
+            if not torch.cuda.is_current_stream_capturing():
+                pr["calls"] += 1  # mirrors the device-side call counter (selects the parity buffer)
             return 1
         _cabi.check(self.lib.impala_clip_adam(
             _ptr(self.params), _ptr(self.comm), _ptr(self.adam_m), _ptr(self.adam_v),
@@ -346,12 +350,16 @@ class LearnerEngine:
                 self._main_launches = self._enqueue_main(slot)
                 if self._one_graph():  # no library collective in between: the optimizer joins the graph
                     self._enqueue_opt()
-            self._graph_main[slot] = g1
+            self._graph_main[(slot, self._parity())] = g1
             if not self._one_graph() and self._graph_opt is None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, stream=self.stream):
                     self._enqueue_opt()
                 self._graph_opt = g2
+
+    def _parity(self) -> int:
+        """Which of this rank's two contribution buffers the next step writes (0 without peers)."""
+        return (self.peer["calls"] + 1) & 1 if self.peer else 0
 
     def _one_graph(self) -> bool:
         """Single GPU, or the optimizer kernel all-reduces over peer memory itself."""
@@ -362,11 +370,14 @@ class LearnerEngine:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.slab_ready[slot])
             if self.use_graph and self.steps_done >= 1:
-                if self._graph_main[slot] is None:
+                key = (slot, self._parity())
+                if key not in self._graph_main:
                     self._capture(slot)
-                self._graph_main[slot].replay()
+                self._graph_main[key].replay()
                 n = self._main_launches
                 fused_opt = self._one_graph()
+                if self.peer:
+                    self.peer["calls"] += 1  # the replayed graph ran impala_allreduce_clip_adam
             else:
                 n = self._enqueue_main(slot)  # first step eager: fills the launch-config caches
                 fused_opt = False
