@@ -121,26 +121,42 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         for (int k = tid; k < 24 * 16; k += kThreads) s_trace[k] = 0;
     TRACE(0, 15)
 
-    // ---- one-time setup
+    // ---- one-time setup.  The mbarriers come first, so that the bulk copies of the first x / dout
+    // tiles are already in flight while every thread stages W1'.
+    if (warp == 18 && lane == 0) {
+        for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
+        for (int s = 0; s < kXStages; ++s) {
+            tc::mbar_init(&bars->full[s], 64);   // every producer thread arrives
+            tc::mbar_init(&bars->empty[s], 1);   // tcgen05.commit after UMMA2
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bars->d1_full[s], 1);           // tcgen05.commit after UMMA1
+            tc::mbar_init(&bars->dp_full[s], nblk * 256);  // every active epilogue thread
+        }
+        tc::mbar_init(&bars->lo_free, 1);  // tcgen05.commit after UMMA2
+        tc::mbar_init(&bars->done, 1);
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    // raw ring: stage i % kRawStages <- x rows (and dout rows) of this CTA's i-th tile, full tiles only
+    auto issue_raw = [&](int i) {
+        const int tile = cta + i * ncta;
+        if ((tile + 1) * kRowsT <= a.M) {
+            const int rs = i % kRawStages;
+            uint8_t* dst = raw + rs * kRawStageBytes;
+            const size_t row0 = (size_t)tile * kRowsT;
+            const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
+            tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
+            tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes_x + bytes_z);
+            tc::bulk_g2s(dst, a.x + row0 * O, bytes_x, &bars->raw_full[rs]);
+            tc::bulk_g2s(dst + kRawDzOffset, a.dout + row0 * a.N2, bytes_z, &bars->raw_full[rs]);
+        }
+    };
+    if (warp == 16 && lane == 0)
+        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
+    if (warp == 18) tc::tmem_alloc(&bars->tmem_base, 512);
     tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/false);
     tc::fence_proxy_async();
-    if (warp == 18) {
-        tc::tmem_alloc(&bars->tmem_base, 512);
-        if (lane == 0) {
-            for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
-            for (int s = 0; s < kXStages; ++s) {
-                tc::mbar_init(&bars->full[s], 64);   // every producer thread arrives
-                tc::mbar_init(&bars->empty[s], 1);   // tcgen05.commit after UMMA2
-            }
-            for (int s = 0; s < 2; ++s) {
-                tc::mbar_init(&bars->d1_full[s], 1);           // tcgen05.commit after UMMA1
-                tc::mbar_init(&bars->dp_full[s], nblk * 256);  // every active epilogue thread
-            }
-            tc::mbar_init(&bars->lo_free, 1);  // tcgen05.commit after UMMA2
-            tc::mbar_init(&bars->done, 1);
-            tc::mbar_fence_init();
-        }
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -262,21 +278,8 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         float gb2[NP];  // db2 = column sums of dout: this thread's rows, combined at the end
 #pragma unroll
         for (int n = 0; n < NP; ++n) gb2[n] = 0.f;
-        const uint32_t bytes_x = kRowsT * O * 4, bytes_z = kRowsT * a.N2 * 4;
         auto tile_of = [&](int i) { return cta + i * ncta; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kRowsT <= a.M; };
-        auto issue_raw = [&](int i) {
-            if (pw == 0 && lane == 0 && is_full(i)) {
-                const int rs = i % kRawStages;
-                uint8_t* dst = raw + rs * kRawStageBytes;
-                const size_t row0 = (size_t)tile_of(i) * kRowsT;
-                tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
-                tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes_x + bytes_z);
-                tc::bulk_g2s(dst, a.x + row0 * O, bytes_x, &bars->raw_full[rs]);
-                tc::bulk_g2s(dst + kRawDzOffset, a.dout + row0 * a.N2, bytes_z, &bars->raw_full[rs]);
-            }
-        };
-        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
         for (int i = 0; i < n_my; ++i) {
             const int s = i % kXStages, ph = (i / kXStages) & 1;
             const int rs = i % kRawStages, rph = (i / kRawStages) & 1;
@@ -310,7 +313,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 }
             }
             asm volatile("bar.sync 1, 64;" ::: "memory");  // both producer warps drained the raw stage
-            if (i + kRawStages < n_my) issue_raw(i + kRawStages);
+            if (pw == 0 && lane == 0 && i + kRawStages < n_my) issue_raw(i + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
             TRACE(i, 7)
             uint8_t* th = x_hi + s * kXTileBytes;

@@ -86,28 +86,43 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
     const float* __restrict__ b2 = a.params + a.lay.ob2;
     const int O = a.O, H = a.H, ochunks = O >> 2;
 
-    // ---- one-time setup: W1' = [W1 | b1 | 0] split into hi/lo swizzled tiles, W2 transposed
+    // ---- one-time setup.  The mbarriers come first, so that the bulk copies of the first x tiles
+    // are already in flight while every thread stages W1' = [W1 | b1 | 0] (hi/lo swizzled tiles)
+    // and W2 (transposed).
+    if (warp == 20 && lane == 0) {
+        for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(&bars->full[s], 4 * 32);  // every producer thread arrives
+            tc::mbar_init(&bars->empty[s], 1);      // tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bars->acc_full[s], 1);         // tcgen05.commit
+            tc::mbar_init(&bars->acc_empty[s], 16 * 32);  // every epilogue thread arrives
+        }
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    const int n_my = (a.num_tiles - cta + ncta - 1) / ncta;
+    // raw ring: stage i % kRawStages <- the x rows of this CTA's i-th tile (full tiles only)
+    auto issue_raw = [&](int i) {
+        const int tile = cta + i * ncta;
+        if ((tile + 1) * kTileM <= a.M) {
+            const int rs = i % kRawStages;
+            const uint32_t bytes = kTileM * O * 4;
+            tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
+            tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes);
+            tc::bulk_g2s(raw + rs * kRawStageBytes, a.x + (size_t)tile * kTileM * O, bytes, &bars->raw_full[rs]);
+        }
+    };
+    if (warp == 16 && lane == 0)
+        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
+    if (warp == 20) tc::tmem_alloc(&bars->tmem_base, 512);
     tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads);
     for (int idx = tid; idx < H * NP; idx += kThreads) {
         const int j = idx / NP, n = idx - j * NP;
         w2s[idx] = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
     }
     tc::fence_proxy_async();
-    if (warp == 20) {
-        tc::tmem_alloc(&bars->tmem_base, 512);
-        if (lane == 0) {
-            for (int s = 0; s < kRawStages; ++s) tc::mbar_init(&bars->raw_full[s], 1);
-            for (int s = 0; s < kStages; ++s) {
-                tc::mbar_init(&bars->full[s], 4 * 32);  // every producer thread arrives
-                tc::mbar_init(&bars->empty[s], 1);      // tcgen05.commit
-            }
-            for (int s = 0; s < 2; ++s) {
-                tc::mbar_init(&bars->acc_full[s], 1);        // tcgen05.commit
-                tc::mbar_init(&bars->acc_empty[s], 16 * 32);  // every epilogue thread arrives
-            }
-            tc::mbar_fence_init();
-        }
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -202,20 +217,8 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
     } else if (warp < 20) {
         // =============================== producer ===============================
         const int r = 32 * (warp - 16) + lane;  // row of the tile this thread converts
-        const int n_my = (a.num_tiles - cta + ncta - 1) / ncta;
         auto tile_of = [&](int i) { return cta + i * ncta; };
         auto is_full = [&](int i) { return (tile_of(i) + 1) * kTileM <= a.M; };
-        auto issue_raw = [&](int i) {
-            if (warp == 16 && lane == 0 && is_full(i)) {
-                const int rs = i % kRawStages;
-                const uint32_t bytes = kTileM * O * 4;
-                tc::fence_proxy_async();  // earlier generic reads of this stage precede the async write
-                tc::mbar_arrive_expect_tx(&bars->raw_full[rs], bytes);
-                tc::bulk_g2s(raw + rs * kRawStageBytes, a.x + (size_t)tile_of(i) * kTileM * O, bytes,
-                             &bars->raw_full[rs]);
-            }
-        };
-        for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
         for (int it = 0; it < n_my; ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
             const int rs = it % kRawStages, rph = (it / kRawStages) & 1;
@@ -242,7 +245,7 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             for (int c = 0; c < 8; ++c)
                 if (c == ochunks) v[c].x = 1.f;  // the column that multiplies b1
             asm volatile("bar.sync 1, 128;" ::: "memory");  // all 4 producer warps drained the raw stage
-            if (it + kRawStages < n_my) issue_raw(it + kRawStages);
+            if (warp == 16 && lane == 0 && it + kRawStages < n_my) issue_raw(it + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMAs that read this stage have retired
             TRACE(it, 7)
             uint8_t* th = x_hi + s * kTileBytes;
