@@ -46,6 +46,12 @@ extern "C" {
 int impala_abi_version(void);
 int impala_compiled_sm(void);
 
+/* Number of kernels this library has launched (or recorded into a capturing stream) since it was
+ * loaded.  Callers difference it around a call sequence to know how many launches the sequence
+ * is - e.g. the paired entry points are one launch where the tensor-core path covers both
+ * networks and up to four otherwise. */
+long long impala_launch_count(void);
+
 /* Parameter-block layout of one MLP.  offsets[4] = float offsets of W1,b1,W2,b2;
  * *total = padded float count of the block (multiple of IMPALA_PARAM_ALIGN). */
 int impala_param_layout(int O, int H, int N2, int64_t offsets[4], int64_t* total);

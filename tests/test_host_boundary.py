@@ -51,7 +51,7 @@ def test_header_symbols_are_exported_and_bound():
     """Every function include/impala_b200.h declares is exported by the .so and has a ctypes
     signature (no compute call is made - there is no GPU here)."""
     hdr = open(os.path.join(ROOT, "include", "impala_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int64_t|int)\s+(impala_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int64_t|long long|int)\s+(impala_\w+)\s*\(", hdr, flags=re.M))
     assert len(declared) >= 11
     assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
     lib = _cabi.lib()

@@ -3,7 +3,11 @@
 
 #include "common.cuh"
 
+long long g_impala_launches = 0;
+
 extern "C" int impala_abi_version(void) { return 1; }
+
+extern "C" long long impala_launch_count(void) { return __atomic_load_n(&g_impala_launches, __ATOMIC_RELAXED); }
 
 extern "C" int impala_compiled_sm(void) { return 100; }
 

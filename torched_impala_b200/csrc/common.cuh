@@ -26,7 +26,13 @@ static inline MlpLayout impala_make_layout(int O, int H, int N2) {
     return l;
 }
 
+// Kernels this library has launched (or recorded into a capturing stream) since it was loaded;
+// defined in abi.cu, read through impala_launch_count().
+extern long long g_impala_launches;
+
+// Called once after every kernel launch of the library.
 static inline int impala_launch_status() {
+    __atomic_fetch_add(&g_impala_launches, 1, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? IMPALA_OK : (int)e;
 }

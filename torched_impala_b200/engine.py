@@ -278,6 +278,7 @@ class LearnerEngine:
     # ------------------------------------------------------------------------ step
     def _enqueue_main(self, slot: int = 0) -> int:
         lib, hp, st = self.lib, self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        launched = lib.impala_launch_count()
         d = self.d_views[slot]
         T, B, O, A = self.T, self.B, self.O, self.A
         p_pi = C.c_void_p(self.params.data_ptr())
@@ -306,23 +307,7 @@ class LearnerEngine:
             obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), g_pi, g_vf, _ptr(self.ws_pi), self.ws_pi_bytes,
             _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
             "impala_mlp_backward_pair")
-        return 1 + self._mlp_launches()
-
-    def _mlp_launches(self) -> int:
-        """Kernels behind the forward pair + backward pair calls (csrc/mlp.cu): one launch each where
-        the tensor-core path covers both networks; otherwise per network one forward and one
-        backward (+ a reduction launch after an FP32 backward)."""
-        import os
-
-        env = os.environ.get
-        tc = env("IMPALA_MLP_TC", "1")[:1] != "0"
-        fwd_ok = lambda H, N2: tc and self.O % 4 == 0 and 4 <= self.O <= 28 and 16 <= H <= 256 and H % 32 == 0 and N2 <= 4
-        bwd_ok = lambda H, N2: tc and self.O % 4 == 0 and 4 <= self.O <= 28 and H in (128, 256) and N2 <= 4
-        pair = env("IMPALA_MLP_PAIR", "1")[:1] != "0" and 2 <= self.A <= 4
-        nets = ((self.H_pi, self.A), (self.H_v, 1))
-        fwd = 1 if pair and all(fwd_ok(H, n) for H, n in nets) else 2
-        bwd = 1 if pair and all(bwd_ok(H, n) for H, n in nets) else sum(1 if bwd_ok(H, n) else 2 for H, n in nets)
-        return fwd + bwd
+        return int(lib.impala_launch_count() - launched)  # kernels actually launched / captured
 
     def _enqueue_opt(self) -> int:
         hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
