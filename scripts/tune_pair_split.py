@@ -29,7 +29,7 @@ eng.load_device_batch(synth.make_batch(1, w["T"], w["B"], w["O"], w["A"]))
 eng.step()
 eng.synchronize()
 buf = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
-for wt in (100, 110, 120, 127, 135, 145, 155, 170, 190):
+for wt in (100, 115, 127, 140, 150, 160, 175, 190, 210):
     os.environ["IMPALA_PAIR_W_FWD"] = os.environ["IMPALA_PAIR_W_BWD"] = str(wt)
     with torch.cuda.stream(eng.stream):
         k = bench.kernel_breakdown(eng, buf.zero_, iters=15)

@@ -19,7 +19,9 @@
 // persistent CTA and is read out once.  K' = 32 floats = one 128-byte swizzle row, so W1', X'
 // and X'^T tiles share one smem format (K-major, SWIZZLE_128B); the producer writes each x tile
 // row-major (B of UMMA1, K = features) and transposed (B of UMMA2, K = batch rows).  Operands
-// are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per K step.
+// are split into tf32 hi + lo and three UMMAs (hi*hi + lo*hi + hi*lo) are issued per K step
+// (x and W1: hi = round-to-nearest tf32; DP: hi = dp with the low 13 mantissa bits cleared - one
+// LOP3 where cvt.rna.tf32 is a four-instruction sequence - and lo = the exact remainder).
 //
 // UMMA2 issues two instead of three products per K step: the x^T tile stacks the hi and lo
 // features as 64 rows, so  DP_hi x [X'^T_hi ; X'^T_lo]  (N = 64) yields dp_hi*x_hi and dp_hi*x_lo

@@ -1,20 +1,22 @@
-"""Host-side step engine of the B200 learner: buffers, streams, CUDA graph, allreduce.
+"""Host-side step engine of the B200 learner: buffers, streams, CUDA graph, peer buffers.
 
 One `LearnerEngine` lives in the learner process of one GPU.  It owns every device
 buffer of the update path and enqueues, per learner step, exactly the C-ABI calls of
 include/impala_b200.h (PyTorch only provides device memory, streams and
 `torch.distributed`):
 
-    impala_ingest          pinned host slab -> device slab (one DMA)      learner.py:104-109,117
-    impala_mlp_forward x2  policy logits (T*B rows), values ((T+1)*B)      learner.py:112-113
-    impala_vtrace_loss     V-trace, 3 losses, dL/dlogits, dL/dv, scalars   learner.py:116-162
-    impala_mlp_backward x2 parameter gradients (float64)                   learner.py:175
-    [all_reduce]           one NCCL sum over [grads | scalars], N > 1 only (new)
-    impala_clip_adam       per-net clip + Adam + step counter              learner.py:176-183
+    impala_ingest              pinned host slab -> device slab (one DMA)        learner.py:104-109,117
+    impala_mlp_forward_pair    policy logits (T*B rows) + values ((T+1)*B)      learner.py:112-113
+    impala_vtrace_loss         V-trace, 3 losses, dL/dlogits, dL/dv, scalars    learner.py:116-162
+    impala_mlp_backward_pair   parameter gradients of both nets (float64)       learner.py:175
+    impala_clip_adam           per-net clip + Adam + step counter               learner.py:176-183
+      N > 1: impala_allreduce_clip_adam - the same kernel first sums [grads | scalars] of all
+      ranks over NVLink peer memory (new).  IMPALA_ALLREDUCE=nccl: torch.distributed
+      all-reduce between the backward and impala_clip_adam instead.
 
-With `use_graph=True` the launch sequence between ingest and the (optional)
-collective, and the optimizer launch after it, are captured once into CUDA graphs and
-replayed each step.  Ingest is double buffered: two pinned host slabs, two device slabs and
+With `use_graph=True` the whole launch sequence of a step is captured once per (slab, parity
+buffer) into ONE CUDA graph and replayed (two graphs around the collective in the NCCL scheme).
+Ingest is double buffered: two pinned host slabs, two device slabs and
 a dedicated copy stream, so the DMA of batch i+1 runs under the kernels of batch i
 (`ingest(slot)` / `step(slot)` order themselves with events); the loss scalars come back
 through a small ring of pinned buffers (`post_scalars` / `fetch_scalars`) so the host only
