@@ -169,7 +169,7 @@ int impala_peer_free(void* dev_ptr);
  * a second handshake: a buffer is rewritten two calls later, after the ready flags of the call
  * in between proved that every peer has finished reading it.  `seq` is a device int64 (zero-filled
  * once) that counts the calls; every rank must make the same sequence of calls.  A rank that
- * never arrives turns into a launch failure (trap after ~4 s) on the others.  Replaces the
+ * never arrives turns into a launch failure (trap after ~35 s) on the others.  Replaces the
  * DistributedDataParallel-style all-reduce a multi-GPU port of learner.py:175-183 would place
  * between loss.backward() and optimizer.step(). */
 int impala_allreduce_clip_adam(float* params, double* reduced, const double* const* peer_contrib,

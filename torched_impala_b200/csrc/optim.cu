@@ -134,7 +134,7 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
 // ready flag for s + 1 - and a peer posts that flag only after its kernel of step s (the one that
 // read the buffer) has finished.
 // Flags are monotonically increasing step numbers (int64, never reset); spins are bounded by a
-// clock timeout that traps (a lost rank becomes a launch failure on the others, not a hang).
+// clock timeout (~35 s) that traps (a lost rank becomes a launch failure on the others, not a hang).
 // Flag block of a rank: int64[world], entry r written by rank r.
 struct PeerArgs {
     const double* const* contrib;  // device array [world]: every rank's 2 x [n_total + n_pad] doubles
@@ -162,7 +162,7 @@ __device__ __forceinline__ void wait_flags(const long long* block, int n, long l
     if (lane < n) {
         const long long t0 = clock64();
         while (ld_acquire_sys(block + lane) < seq)
-            if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: a peer is gone
+            if (clock64() - t0 > (1ll << 36)) __trap();  // ~35 s: a peer is gone
     }
     __syncwarp();
 }
