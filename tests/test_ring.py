@@ -16,7 +16,7 @@ def _writer(ring, first, count, seed):
     trajs = synth.to_trajectories(batch)
     for i in range(first, first + count):
         tr = trajs[i]
-        tr.id = (seed, i)
+        tr.id = 1000 * seed + i
         ring.put(tr, timeout=30)
 
 
@@ -33,7 +33,7 @@ def test_two_writer_processes_fill_slabs_in_learner_layout():
             k, reward = ring.collect_batch(timeout=30)
             v = ring.views(k)
             for b in range(B):
-                seed, i = ring.ids[k][b]
+                seed, i = divmod(ring.ids[k][b], 1000)
                 assert seed == 3 and i not in seen
                 seen.add(i)
                 for name in ("obs", "beh_logits", "actions", "rewards", "done"):

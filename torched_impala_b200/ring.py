@@ -3,17 +3,21 @@
 The reference ships every trajectory through `mp.Queue` as ~5T+1 separately pickled tiny tensors
 (one file descriptor each, `utils.py:48-77`, `actor.py:116-124`): about 52 ms per trajectory at
 the consumer and an fd-exhaustion failure mode.  `RingQueue` keeps the queue
-interface the unmodified `actor.py` uses (`q.put(traj, timeout=...)`, `queue.Full`), but the
-payload never travels through the pipe:
+interface the unmodified `actor.py` uses (`q.put(traj, timeout=...)`, `queue.Full`), but nothing
+travels through a pipe any more - payload AND bookkeeping live in one
+`multiprocessing.shared_memory` segment:
 
-  * K batch slabs live in ONE `multiprocessing.shared_memory` segment, each in exactly the
-    learner's device layout (time-major, float32, `impala_batch_layout` offsets);
-  * `put()` runs in the ACTOR process: it takes a free (slab, column) ticket, packs the trajectory
-    straight into that column with the same `pack_trajectory` the learner uses, and posts the
-    ticket (three small ints) on a control queue;
-  * the learner collects tickets until a slab is complete; with a GPU it registers the segment
-    with `cudaHostRegister` once and DMAs each finished slab to the device directly - no second
-    host copy, no per-tensor pickling.
+  * K batch slabs, each in exactly the learner's device layout (time-major, float32,
+    `impala_batch_layout` offsets);
+  * a control block: one "column filled" byte, the reward sum and the trajectory id per
+    (slab, column), a release counter per slab, and the next ticket number.
+
+`put()` runs in the ACTOR process: under a lock it takes the next ticket n (slab (n // B) % K,
+column n % B; only once the learner has released that slab often enough), packs the trajectory
+straight into that column with the same `pack_trajectory` the learner uses, and sets the column's
+byte.  The learner polls B bytes per batch - no per-trajectory message, no pickling - and, with a
+GPU, registers the segment with `cudaHostRegister` once and DMAs each finished slab to the device
+directly (no second host copy).
 
 `train.py` changes one line (`q = RingQueue(...)` instead of `mp.Queue(...)`); `Learner` detects
 the ring by its `collect_batch` method and otherwise speaks the reference wire format.
@@ -21,6 +25,7 @@ the ring by its `collect_batch` method and otherwise speaks the reference wire f
 from __future__ import annotations
 
 import queue
+import threading
 import time
 from multiprocessing import shared_memory
 
@@ -29,6 +34,7 @@ import torch.multiprocessing as mp
 
 _FIELDS = (("obs", np.float32), ("beh_logits", np.float32), ("actions", np.int32),
            ("rewards", np.float32), ("done", np.uint8), ("lens", np.int32))
+_POLL_S = 2e-4
 
 
 def _layout(T: int, B: int, O: int, A: int):
@@ -50,32 +56,49 @@ class RingQueue:
             raise ValueError("need at least two slabs (one filling while one is consumed)")
         self.T, self.B, self.O, self.A, self.K = T, B, O, A, slabs
         self.offsets, self.slab_bytes = _layout(T, B, O, A)
-        self.shm = shared_memory.SharedMemory(create=True, size=self.slab_bytes * slabs)
+        # control block after the slabs: filled u8[K][B] | rsum f64[K][B] | tid i64[K][B] |
+        # released i64[K] | next_ticket i64[1]   (8-byte aligned pieces)
+        kb = slabs * B
+        self._ctl_off = self.slab_bytes * slabs
+        self._ctl = {"filled": (0, np.uint8, (slabs, B))}
+        off = (kb + 7) // 8 * 8
+        for name, dt, shape in (("rsum", np.float64, (slabs, B)), ("tid", np.int64, (slabs, B)),
+                                ("released", np.int64, (slabs,)), ("ticket", np.int64, (1,))):
+            self._ctl[name] = (off, dt, shape)
+            off += int(np.prod(shape)) * 8
+        self.shm = shared_memory.SharedMemory(create=True, size=self._ctl_off + off)
         self._owner = True
-        self.free = mp.Queue()    # (slab, column) tickets an actor may fill
-        self.ready = mp.Queue()   # (slab, column, reward_sum) tickets that are filled
-        for k in range(slabs):
-            for b in range(B):
-                self.free.put((k, b))
+        self._lock = mp.Lock()          # serialises ticket allocation between actors
         self._views = None
-        self._counts = [0] * slabs
-        self._rewards = [0.0] * slabs
-        self.ids = [[None] * B for _ in range(slabs)]  # trajectory id per (slab, column), for logs
+        self._c = None
+        self._fence = threading.Lock()  # acquire/release = a full memory fence on every platform
         self._next = 0
+        self.ids = [[None] * B for _ in range(slabs)]  # trajectory id per (slab, column), for logs
+        c = self._control()
+        c["filled"][:] = 0
+        c["released"][:] = 0
+        c["ticket"][0] = 0
 
     # ---- pickling: child processes attach to the same segment by name
     def __getstate__(self):
         d = self.__dict__.copy()
-        d["_views"] = None
+        d["_views"] = d["_c"] = None
         d["_owner"] = False
         d["shm_name"] = self.shm.name
-        del d["shm"]
+        del d["shm"], d["_fence"]
         return d
 
     def __setstate__(self, d):
         name = d.pop("shm_name")
         self.__dict__.update(d)
+        self._fence = threading.Lock()
         self.shm = shared_memory.SharedMemory(name=name)
+
+    def _control(self) -> dict:
+        if self._c is None:
+            self._c = {name: np.ndarray(shape, dtype=dt, buffer=self.shm.buf, offset=self._ctl_off + off)
+                       for name, (off, dt, shape) in self._ctl.items()}
+        return self._c
 
     def views(self, k: int) -> dict:
         """Numpy views of slab k (the six batch tensors, learner layout)."""
@@ -86,52 +109,75 @@ class RingQueue:
             self._views = []
             for kk in range(self.K):
                 base = kk * self.slab_bytes
-                v = {}
-                for (name, dt), off in zip(_FIELDS, self.offsets):
-                    n = int(np.prod(shapes[name]))
-                    v[name] = np.ndarray(shapes[name], dtype=dt, buffer=self.shm.buf, offset=base + off)
-                    assert v[name].size == n
-                self._views.append(v)
+                self._views.append({name: np.ndarray(shapes[name], dtype=dt, buffer=self.shm.buf, offset=base + off)
+                                    for (name, dt), off in zip(_FIELDS, self.offsets)})
         return self._views[k]
 
     def slab_address(self, k: int) -> int:
         """Address of slab k in THIS process (for cudaHostRegister / impala_ingest)."""
         return np.ndarray((1,), dtype=np.uint8, buffer=self.shm.buf, offset=k * self.slab_bytes).ctypes.data
 
+    def _barrier(self) -> None:
+        with self._fence:
+            pass
+
     # ---- actor side (same call shape as mp.Queue.put used at actor.py:118)
     def put(self, traj, block: bool = True, timeout: float | None = None):
         from .learner import pack_trajectory
 
-        try:
-            k, b = self.free.get(block, timeout)
-        except queue.Empty:
-            raise queue.Full from None
+        c = self._control()
+        end = None if (timeout is None or not block) else time.monotonic() + timeout
+        while True:
+            with self._lock:
+                n = int(c["ticket"][0])
+                k, b, gen = (n // self.B) % self.K, n % self.B, n // (self.B * self.K)
+                if int(c["released"][k]) >= gen:  # the learner has handed slab k out `gen` times
+                    c["ticket"][0] = n + 1
+                    break
+            if not block or (end is not None and time.monotonic() >= end):
+                raise queue.Full  # like mp.Queue.put on a full queue; actor.py:120 retries
+            time.sleep(_POLL_S)
         rsum = pack_trajectory(self.views(k), b, traj, self.T)
-        self.ready.put((k, b, rsum, getattr(traj, "id", None)))
+        tid = getattr(traj, "id", None)
+        c["rsum"][k, b] = rsum
+        c["tid"][k, b] = int(tid) if isinstance(tid, (int, np.integer)) else -1
+        self._barrier()  # payload before the flag
+        c["filled"][k, b] = 1
 
     # ---- learner side
     def collect_batch(self, timeout: float | None = None):
         """Blocks until the next slab (in round-robin order) has all B columns; returns
-        (slab index, batch-mean reward).  Raises queue.Empty after `timeout` seconds without a
-        ticket, like `mp.Queue.get` does for the reference learner (learner.py:91-100)."""
-        k = self._next
-        while self._counts[k] < self.B:
-            kk, bb, rsum, tid = self.ready.get(True, timeout)
-            self._counts[kk] += 1
-            self._rewards[kk] += rsum / self.B
-            self.ids[kk][bb] = tid
-        reward, self._counts[k], self._rewards[k] = self._rewards[k], 0, 0.0
+        (slab index, batch-mean reward).  Raises queue.Empty when no new trajectory has arrived
+        for `timeout` seconds, like `mp.Queue.get` does for the reference learner
+        (learner.py:91-100)."""
+        c, k = self._control(), self._next
+        seen, last = -1, time.monotonic()
+        while True:
+            n = int(np.count_nonzero(c["filled"][k]))
+            if n == self.B:
+                break
+            now = time.monotonic()
+            if n != seen:
+                seen, last = n, now
+            elif timeout is not None and now - last >= timeout:
+                raise queue.Empty
+            time.sleep(_POLL_S)
+        self._barrier()  # flags before the payload reads
+        reward = float(c["rsum"][k].sum()) / self.B
+        self.ids[k] = [int(t) if t >= 0 else None for t in c["tid"][k]]
         self._next = (k + 1) % self.K
         return k, reward
 
     def release(self, k: int) -> None:
         """The learner is done with slab k (its DMA has completed): hand its columns out again."""
-        for b in range(self.B):
-            self.free.put((k, b))
+        c = self._control()
+        c["filled"][k] = 0
+        self._barrier()
+        c["released"][k] += 1
 
     def close(self):
         try:
-            self._views = None
+            self._views = self._c = None
             self.shm.close()
             if self._owner:
                 self.shm.unlink()
