@@ -48,6 +48,52 @@ def test_two_writer_processes_fill_slabs_in_learner_layout():
         ring.close()
 
 
+def _stream_writer(ring, wid, count):
+    trajs = synth.to_trajectories(synth.make_batch(10 + wid, T, count, O, A, ragged=True))
+    for i, tr in enumerate(trajs):
+        tr.id = 1000 * wid + i
+        while True:
+            try:
+                ring.put(tr, timeout=0.05)  # short timeout: exercises the queue.Full retry of actor.py:116-124
+                break
+            except queue.Full:
+                continue
+
+
+def test_many_generations_lose_and_duplicate_nothing():
+    """Three writers, two slabs of four columns, ten generations per slab: every trajectory
+    arrives exactly once, intact, whichever writer got which ticket."""
+    ctx = mp.get_context("fork")
+    Bs, per = 4, 28  # 84 trajectories = 21 batches
+    ring = RingQueue(T, Bs, O, A, slabs=2)
+    try:
+        ps = [ctx.Process(target=_stream_writer, args=(ring, w, per)) for w in range(3)]
+        for p in ps:
+            p.start()
+        want = {w: synth.make_batch(10 + w, T, per, O, A, ragged=True) for w in range(3)}
+        seen = set()
+        for _ in range(3 * per // Bs):
+            k, reward = ring.collect_batch(timeout=30)
+            v = ring.views(k)
+            total = 0.0
+            for b in range(Bs):
+                w, i = divmod(ring.ids[k][b], 1000)
+                assert (w, i) not in seen
+                seen.add((w, i))
+                np.testing.assert_array_equal(v["obs"][:, b], want[w]["obs"][:, i])
+                np.testing.assert_array_equal(v["actions"][:, b], want[w]["actions"][:, i])
+                assert v["lens"][b] == want[w]["lens"][i]
+                total += float(want[w]["rewards"][:, i].astype(np.float64).sum())
+            assert abs(reward - total / Bs) < 1e-9
+            ring.release(k)
+        assert len(seen) == 3 * per
+        for p in ps:
+            p.join(timeout=10)
+            assert p.exitcode == 0
+    finally:
+        ring.close()
+
+
 def test_full_ring_raises_queue_full_like_mp_queue():
     ring = RingQueue(T, 2, O, A, slabs=2)
     try:
