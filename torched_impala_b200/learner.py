@@ -53,13 +53,13 @@ def pack_trajectory(views: dict, b: int, traj, T: int) -> float:
     views["beh_logits"][L:, b] = 0
     views["actions"][:L, b] = torch.stack(traj.a).reshape(L).to(torch.int32).numpy()
     views["actions"][L:, b] = 0
-    r = torch.stack(traj.r).to(torch.float32).numpy()
-    views["rewards"][:L, b] = r
+    r = torch.stack(traj.r)
+    views["rewards"][:L, b] = r.to(torch.float32).numpy()
     views["rewards"][L:, b] = 0
     views["done"][:L, b] = torch.stack(traj.d).to(torch.uint8).numpy()
     views["done"][L:, b] = 0
     views["lens"][b] = L
-    return float(r.sum(dtype=np.float64))
+    return float(r.sum(dtype=torch.float64))  # summed as received (float64 from actor.py), like learner.py:108
 
 
 def _dims(policy, value_fn):
