@@ -138,3 +138,27 @@ def test_unmodified_reference_actor_feeds_the_packer():
     for k in ("value_fn_loss", "policy_loss", "policy_entropy", "total_loss", "batch_mean_reward"):
         # the packed batch is float32, the wire format float64: rounding of obs/logits only
         assert abs(port[k] - dense[k]) < 1e-5 * max(1.0, abs(port[k])), (k, port[k], dense[k])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/impala_b200.h is the drop-in boundary: it must compile as C99 (and as C++) on its own,
+    and a C program must link against the shared library through it."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include <stdio.h>\n#include "impala_b200.h"\n'
+                   'int main(void) { int64_t off[4], total; int rc = impala_param_layout(24, 256, 4, off, &total);\n'
+                   '  printf("%d %d %lld\\n", impala_abi_version(), rc, (long long)total); return rc; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-limpala_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "1" and out[1] == "0"
+    assert int(out[2]) == _cabi.param_layout(24, 256, 4)[1]
