@@ -30,10 +30,36 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(T=20, B=4096, O=24, A=4, H=256)
-WORKLOAD_NAME = "c4: synthetic obs=24 act=4 hidden=256, T=20 B=4096 (BASELINE.json configs[3])"
+# BASELINE.json configs[2..4]; c4 is the configuration the metric is quoted on (the default).
+WORKLOADS = {
+    "c3": dict(T=20, B=1024, O=24, A=4, H=256,
+               name="c3: synthetic obs=24 act=4 hidden=256, T=20 B=1024 (BASELINE.json configs[2])"),
+    "c4": dict(T=20, B=4096, O=24, A=4, H=256,
+               name="c4: synthetic obs=24 act=4 hidden=256, T=20 B=4096 (BASELINE.json configs[3])"),
+    "c5": dict(T=100, B=8192, O=64, A=4, H=512,
+               name="c5: long-unroll stress obs=64 act=4 (assumed, SURVEY 8) hidden=512, T=100 B=8192 (BASELINE.json configs[4])"),
+}
+WORKLOAD = {k: v for k, v in WORKLOADS["c4"].items() if k != "name"}
+WORKLOAD_NAME = WORKLOADS["c4"]["name"]
 METRIC = "learner steps/sec on synthetic (T=20,B=4096) trajectories"
 SMS, FP32_LANES = 148, 128
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def select_workload(cfg: str) -> None:
+    global WORKLOAD, WORKLOAD_NAME, METRIC
+    WORKLOAD = {k: v for k, v in WORKLOADS[cfg].items() if k != "name"}
+    WORKLOAD_NAME = WORKLOADS[cfg]["name"]
+    METRIC = f"learner steps/sec on synthetic (T={WORKLOAD['T']},B={WORKLOAD['B']}) trajectories"
 
 
 def peaks():
@@ -54,60 +80,124 @@ def hparams(B):
 
 
 # --------------------------------------------------------------------------- CPU baseline
-def time_cpu_port(sample_B: int, warm: int, timed: int, threads: int):
-    """Per-trajectory float64 port of learner.py:75-183 on `threads` host threads."""
+class _TimedCounter:
+    """utils.Counter stand-in (learner.py:254-255) that stamps the wall clock at every update."""
+
+    def __init__(self):
+        self.n, self.stamps = 0, [time.perf_counter()]
+
+    def increment(self):
+        self.n += 1
+        self.stamps.append(time.perf_counter())
+
+    @property
+    def value(self):
+        return self.n
+
+
+def time_reference_learner(sample_B: int, warm: int, timed: int, threads: int):
+    """The UNMODIFIED reference `Learner._learn` (learner.py:67-275) from oracle/_ref (or
+    /root/reference), driven in-process through a list-backed queue; returns (median seconds per
+    update, kind).  Falls back to the float64 per-trajectory port when the reference is absent."""
     import torch
 
-    from oracle.cpu_learner_port import CpuLearnerPort
+    from oracle import refload
     from torched_impala_b200 import synth
 
     w = WORKLOAD
-    hp = hparams(sample_B)
-    port = CpuLearnerPort(synth.init_params(0, w["O"], w["A"], w["H"]), hp, threads=threads)
-    trajs = synth.to_trajectories(synth.make_batch(1, w["T"], sample_B, w["O"], w["A"]))
-    times = []
-    for i in range(warm + timed):
-        t0 = time.perf_counter()
-        port.update(trajs)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    return statistics.median(times)
+    torch.set_num_threads(threads)
+    batch = synth.make_batch(1, w["T"], sample_B, w["O"], w["A"])
+    trajs = synth.to_trajectories(batch)
+    params = synth.init_params(0, w["O"], w["A"], w["H"])
+    n = warm + timed
+    if refload.available():
+        ref_learner, ref_models, ref_utils = refload.load()
+        hp = ref_utils.Hyperparameters(**hparams(sample_B)._replace(
+            max_updates=n, eval_every=None, save_every=10 ** 9, verbose=0, log_path=None)._asdict())
+        pol = ref_models.MlpPolicy(w["O"], w["A"], w["H"])
+        vf = ref_models.MlpValueFn(w["O"], w["H"])
+        for mod, grp in ((pol, "policy"), (vf, "value_fn")):
+            mod.load_state_dict({k: torch.from_numpy(v).double() for k, v in params[grp].items()})
+            mod.eval()  # the parity setting (SURVEY 0.4): Dropout(p=0.8) off
+        cnt = _TimedCounter()
+        lrn = ref_learner.Learner(1, hp, pol, vf, refload.ListQueue(trajs * n), cnt, None, timeout=1)
+        cnt.stamps[0] = time.perf_counter()
+        lrn._learn()
+        times = [b - a for a, b in zip(cnt.stamps[:-1], cnt.stamps[1:])][warm:]
+        kind = "reference"
+    else:
+        from oracle.cpu_learner_port import CpuLearnerPort
+
+        port = CpuLearnerPort(params, hparams(sample_B), threads=threads)
+        times = []
+        for i in range(n):
+            t0 = time.perf_counter()
+            port.update(trajs)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+        kind = "port"
+    return statistics.median(times), kind
 
 
-def cpu_baseline(sample_B=512, warm=1, timed=3):
-    """1 torch thread on the full sample; all host threads probed on a small sample first -
-    the per-trajectory python loop gets slower with more threads (tiny ops, thread thrash), so the
-    many-thread run is only repeated at full sample size if the probe says it could win."""
+def cpu_reference_numbers(warm: int, timed: int, budget_s: float = 120.0):
+    """Times the reference CPU learner on this host.  Full batch when it fits `budget_s`, otherwise
+    a bounded sample of trajectories scaled linearly (the reference loops over trajectories,
+    learner.py:89: cost is linear in B) and labelled as such."""
     cores = os.cpu_count() or 1
-    t1 = time_cpu_port(sample_B, warm, timed, 1)
-    probe_B = 32
-    tn_probe = time_cpu_port(probe_B, 1, 1, cores) * (sample_B / probe_B) if cores > 1 else t1
-    tn = time_cpu_port(sample_B, warm, timed, cores) if tn_probe < t1 else tn_probe
-    best_t, best_c = (t1, 1) if t1 <= tn else (tn, cores)
-    scale = WORKLOAD["B"] / sample_B  # cost is linear in B (python loop over trajectories)
-    return dict(value=1.0 / (best_t * scale), unit="steps/s", cores=best_c, kind="port",
-                sample=(f"oracle/cpu_learner_port.py, {warm}+{timed} updates of B={sample_B} "
-                        f"(T=20,O=24,H=256), median, scaled x{scale:g} to B=4096 (cost linear in B); "
-                        f"1 thread {t1 * 1e3:.0f} ms per B={sample_B} update; {cores} threads "
-                        f"{tn * 1e3:.0f} ms ({'measured' if tn_probe < t1 else f'extrapolated from a B={probe_B} probe'})"),
-                host_cores=cores)
+    w = WORKLOAD
+    probe_B = min(32, w["B"])
+    t1, kind = time_reference_learner(probe_B, 1, 1, 1)
+    tn, _ = time_reference_learner(probe_B, 1, 1, cores) if cores > 1 else (t1, kind)
+    threads, per_traj = (1, t1 / probe_B) if t1 <= tn else (cores, tn / probe_B)
+    sample_B = w["B"]
+    while sample_B > 64 and per_traj * sample_B * (warm + timed) > budget_s:
+        sample_B //= 2
+    t, kind = time_reference_learner(sample_B, warm, timed, threads)
+    scale = w["B"] / sample_B
+    from oracle import refload
+
+    what = (f"the unmodified reference Learner._learn ({os.path.relpath(refload.reference_dir(), ROOT) if refload.reference_dir().startswith(ROOT) else refload.reference_dir()}, "
+            "eval mode, in-process list queue)" if kind == "reference"
+            else "oracle/cpu_learner_port.py (float64 per-trajectory port; reference modules not found)")
+    return dict(value=1.0 / (t * scale), unit="steps/s", cores=threads, kind=kind, host_cores=cores,
+                sample=(f"{what}: {warm}+{timed} updates of B={sample_B} (T={w['T']},O={w['O']},H={w['H']}), median"
+                        + (f", scaled x{scale:g} to B={w['B']} (cost linear in B)" if scale != 1 else ", full batch")
+                        + f"; probe at B={probe_B}: 1 thread {t1 * 1e3:.0f} ms, {cores} threads {tn * 1e3:.0f} ms per update"),
+                sample_B=sample_B, timed_updates=timed, ms_per_update_sample=t * 1e3)
+
+
+def reference_line(args, cb, steps, warm):
+    w = WORKLOAD
+    return dict(metric=METRIC, value=cb["value"], unit="steps/s", n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD_NAME, **w, global_batch=w["B"], per_gpu_batch=w["B"] // max(1, args.gpus)),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    cb = cpu_baseline(sample_B=512, warm=warm, timed=steps)
-    line = dict(metric=METRIC, value=cb["value"], unit="steps/s", n_gpus=args.gpus, steps=steps,
-                warmup=warm, ms_per_step=1e3 / cb["value"], higher_is_better=True, scaling="strong",
-                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD_NAME, **WORKLOAD, global_batch=WORKLOAD["B"]),
-                cpu_baseline=cb,
-                e2e=dict(value=cb["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference picks its device at import (learner.py:13)
+    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+    cb = cpu_reference_numbers(warm, steps)
+    emit(reference_line(args, cb, steps, warm))
+
+
+def cpu_baseline(config: str):
+    """`cpu_baseline` of the own arm: the reference arm in a fresh CPU-only subprocess (this process
+    has CUDA initialised; the reference resolves its device at import), 1 + 3 updates."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", config,
+                          "--steps", "3", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(res.stdout.splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu_baseline subprocess printed no JSON line:\n" + res.stderr[-2000:])
 
 
 # --------------------------------------------------------------------------------- clocks
@@ -309,9 +399,20 @@ def run_own_arm(args):
     hp = hparams(w["B"])
     eng = LearnerEngine(w["T"], Bl, w["O"], w["A"], w["H"], w["H"], hp, global_batch=w["B"],
                         device=f"cuda:{local}", process_group=pg, use_graph=not args.no_graph)
-    eng.load_state(synth.init_params(0, w["O"], w["A"], w["H"]))
+    params0 = synth.init_params(0, w["O"], w["A"], w["H"])
     batches = [synth.shard_batch(synth.make_batch(1 + i, w["T"], w["B"], w["O"], w["A"]), rank, world)
                for i in range(2)]
+    # ---------------- parity of this very configuration (checker, outside every timed region):
+    # one step from the initial parameters on batch 0 against the float64 oracle (oracle/check.py);
+    # with N ranks every rank checks its shard and the oracle sums are all-reduced.
+    parity = None
+    if not args.no_parity:
+        from oracle.check import first_step_parity
+
+        t_par = time.perf_counter()
+        parity = first_step_parity(eng, params0, batches[0], group=pg)
+        parity["seconds"] = round(time.perf_counter() - t_par, 2)
+    eng.load_state(params0)
     for i, b in enumerate(batches):
         eng.fill_host(b, i)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)  # 2x the 126 MB L2
@@ -463,6 +564,34 @@ def run_own_arm(args):
     roofline = dict(kernel=dom, traffic=traffic, peak_source=src,
                     **{k: kernels[dom][k] for k in kernels[dom] if k not in ("us", "in_step")})
 
+    # ---------------- weak scaling beside the strong line: B per GPU = the full workload batch
+    weak = None
+    if world > 1 and not args.no_weak:
+        hp_w = hparams(w["B"] * world)
+        eng_w = LearnerEngine(w["T"], w["B"], w["O"], w["A"], w["H"], w["H"], hp_w, global_batch=w["B"] * world,
+                              device=f"cuda:{local}", process_group=pg, use_graph=not args.no_graph)
+        eng_w.load_state(params0)
+        eng_w.load_device_batch(synth.make_batch(100 + rank, w["T"], w["B"], w["O"], w["A"]))
+        with torch.cuda.stream(eng_w.stream):
+            for _ in range(max(3, args.warmup)):
+                flush()
+                eng_w.step()
+        barrier()
+        evw = []
+        with torch.cuda.stream(eng_w.stream):
+            for _ in range(args.steps):
+                flush()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(eng_w.stream)
+                eng_w.step()
+                e1.record(eng_w.stream)
+                evw.append((e0, e1))
+        barrier()
+        ms_w = max_over_ranks(sum(a.elapsed_time(b) for a, b in evw)) / args.steps
+        weak = dict(scaling="weak", per_gpu_batch=w["B"], global_batch=w["B"] * world, ms_per_step=ms_w,
+                    steps_per_s=1e3 / ms_w, trajectories_per_s=1e3 / ms_w * w["B"] * world,
+                    note="same step with B per GPU = the workload's full batch; value of the line stays the strong-scaling number")
+        del eng_w
     if world > 1:
         import torch.distributed as dist
 
@@ -473,7 +602,7 @@ def run_own_arm(args):
 
             dist.destroy_process_group()
         return
-    cb = cpu_baseline() if world == 1 and not args.no_cpu else None
+    cb = cpu_baseline(args.config) if world == 1 and not args.no_cpu else None
     ms = dev_ms / args.steps
     line = dict(
         metric=METRIC, value=1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps,
@@ -493,10 +622,13 @@ def run_own_arm(args):
                        "copy of batch i+1 overlaps compute of batch i (double-buffered slabs)")),
         roofline=roofline, kernels=kernels,
         loss=dict(device_resident=scal_dev["total_loss"], e2e_last=last["total_loss"]),
+        parity=parity,
     )
+    if weak:
+        line["weak_scaling"] = weak
     if cb:
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -507,9 +639,10 @@ def main():
     # Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON
     # line there.  Keep the real stdout aside, point fd 1 at stderr for the duration of the run
     # and emit the JSON line through the saved descriptor.
-    real_stdout = os.fdopen(os.dup(1), "w")
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    sys.stdout = real_stdout
+    sys.stdout = sys.stderr  # python-level prints (the reference learner is chatty) go to stderr too
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -517,12 +650,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS), help="BASELINE.json config (default: c4, the metric's)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the first-step oracle check")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
     args = ap.parse_args()
+    select_workload(args.config)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_own_arm(args)
-    real_stdout.flush()
+    _REAL_STDOUT.flush()
 
 
 if __name__ == "__main__":

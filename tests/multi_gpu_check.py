@@ -17,6 +17,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+from oracle.check import first_step_parity  # noqa: E402
 from torched_impala_b200 import synth  # noqa: E402
 from torched_impala_b200.engine import LearnerEngine  # noqa: E402
 from torched_impala_b200.utils import default_hparams  # noqa: E402
@@ -32,7 +33,13 @@ def main():
     batches = [synth.make_batch(10 + u, T, B, O, A, ragged=(u == 1)) for u in range(3)]
     eng = LearnerEngine(T, B // world, O, A, H, H, hp, global_batch=B, device=f"cuda:{local}",
                         process_group=dist.group.WORLD)
+    # (1) against the float64 oracle of the FULL batch: every rank checks its shard's vs / pg_adv,
+    # the oracle's scalar and gradient sums are all-reduced (oracle/check.py)
+    par = first_step_parity(eng, params, synth.shard_batch(batches[0], rank, world), group=dist.group.WORLD)
+    assert par["ok"], par
+    # (2) against the single-GPU engine on the full batch, several updates
     eng.load_state(params)
+    eng.adam_m.zero_(), eng.adam_v.zero_(), eng.adam_step.zero_()
     scal = []
     for u, b in enumerate(batches):
         eng.fill_host(synth.shard_batch(b, rank, world), u % 2)
@@ -58,7 +65,8 @@ def main():
         d = (mine - ref.params).abs().max().item()
         assert d < 2e-5, d
         print(f"MULTI_GPU_OK world={world} allreduce={'peer' if eng.peer else 'nccl'} max|dparam|={d:.2e} "
-              f"loss={scal[-1]['total_loss']:.6f}")
+              f"loss={scal[-1]['total_loss']:.6f} oracle: max|dvs|={par['max_abs_vs']:.1e} max|dscalar|={par['max_abs_scalar']:.1e} "
+              f"rel|dgrad|={par['max_rel_grad']:.1e}")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -21,13 +21,18 @@ def run_bench(*args, timeout):
 
 
 def test_reference_arm_line():
-    """`--impl reference`: the CPU port of learner.py on a bounded sample of the same workload."""
-    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", timeout=600)
+    """`--impl reference`: the unmodified reference learner (oracle/_ref or /root/reference; the
+    float64 port only where neither exists) on the same workload, here the small c3 config."""
+    from oracle import refload
+
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--config", "c3", timeout=600)
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "steps/s"
     assert d["value"] > 0 and d["steps"] == 1 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["kind"] == ("reference" if refload.available() else "port")
+    assert cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["config"]["B"] == 1024 and d["config"]["global_batch"] == 1024
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
 
 
@@ -45,3 +50,5 @@ def test_own_arm_line():
     assert d["gpu_launches"] >= 3 * d["steps"]
     assert d["clocks"]["sm_max_mhz"] > 0 and d["clocks"]["sm_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
     assert sum(1 for k in d["kernels"].values() if k.get("in_step")) >= 3
+    par = d["parity"]  # first step of this configuration against the float64 oracle (oracle/check.py)
+    assert par["ok"] and par["max_abs_vs"] < 1e-5 and par["max_abs_pg"] < 1e-5 and par["max_abs_scalar"] < 1e-5, par
