@@ -259,8 +259,13 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------- own arm
-def kernel_breakdown(eng, flush, iters=20):
-    """CUDA-event time of every C-ABI launch of one step, eager, L2 flushed before each."""
+def kernel_breakdown(eng, flush, iters=20, barrier=lambda: None):
+    """CUDA-event time of every C-ABI launch of one step, eager, L2 flushed before each.
+
+    N > 1 (push all-reduce): every rank runs the same call sequence; the backward is timed in its
+    pushing variant (re-posting the current step's contribution is idempotent) and every timed
+    optimizer call is preceded by an untimed stand-alone push, so its time includes the wait for
+    the slowest peer's flag - the real cost of the exchange."""
     import ctypes as C
 
     import torch
@@ -280,9 +285,13 @@ def kernel_breakdown(eng, flush, iters=20):
     calls = {
         "mlp_forward_pair(policy+value_fn)": lambda: lib.impala_mlp_forward_pair(
             obs, p_pi, p_vf, _ptr(eng.logits), _ptr(eng.values), eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, st),
-        "mlp_backward_pair(policy+value_fn)": lambda: lib.impala_mlp_backward_pair(
+        "mlp_backward_pair(policy+value_fn)": (lambda: lib.impala_mlp_backward_pair_push(
+            obs, p_pi, p_vf, _ptr(eng.dlogits), _ptr(eng.dv), _ptr(eng.ws_pi), eng.ws_pi_bytes, _ptr(eng.ws_vf),
+            eng.ws_vf_bytes, eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, scal, 4, _ptr(eng.peer["gather_ptrs"]),
+            _ptr(eng.peer["flag_ptrs"]), _ptr(eng.peer["seq"]), eng.peer["slot"], eng.peer["buf"], eng.peer["rank"],
+            eng.world, st)) if (eng.peer and eng.peer["fused"]) else (lambda: lib.impala_mlp_backward_pair(
             obs, p_pi, p_vf, _ptr(eng.dlogits), _ptr(eng.dv), g_pi, g_vf, _ptr(eng.ws_pi), eng.ws_pi_bytes,
-            _ptr(eng.ws_vf), eng.ws_vf_bytes, eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, st),
+            _ptr(eng.ws_vf), eng.ws_vf_bytes, eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, st)),
         # the per-network entry points, for comparison (not launched by the step)
         "mlp_forward(policy)": lambda: lib.impala_mlp_forward(obs, p_pi, _ptr(eng.logits), eng.M_pi, O, eng.H_pi, A, st),
         "mlp_forward(value_fn)": lambda: lib.impala_mlp_forward(obs, p_vf, _ptr(eng.values), eng.M_vf, O, eng.H_v, 1, st),
@@ -314,6 +323,7 @@ def kernel_breakdown(eng, flush, iters=20):
     out = {}
     with torch.cuda.stream(eng.stream):
         for name, fn in calls.items():
+            barrier()
             ts = []
             for _ in range(iters):
                 flush()
@@ -354,10 +364,20 @@ def kernel_breakdown(eng, flush, iters=20):
             bytes=4.0 * Tl * Bl2 * (2 * Al + 2) + Tl * Bl2 + 4.0 * (Tl + 1) * Bl2 + 4.0 * (Tl + 1) * Bl2 + 4.0 * Tl * Bl2)
         del cur, beh, act, rew, don, lens_l, vv, vs_o, pg_o
         # optimizer: needs a valid gradient in comm; time it on copies so parameters stay intact
-        ts = []
+        barrier()
+        ts, ts_push = [], []
         keep = [t.clone() for t in (eng.params, eng.adam_m, eng.adam_v, eng.adam_step)]
+        pr = eng.peer
         for _ in range(iters):
             flush()
+            if pr:  # this step's contribution -> every rank (stand-alone producer), timed on its own
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(eng.stream)
+                _cabi.check(lib.impala_peer_push(_ptr(eng.comm), eng.n_total + 8, _ptr(pr["gather_ptrs"]),
+                                                 _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"],
+                                                 eng.world, _ptr(pr["ctl"]), st), "impala_peer_push")
+                e1.record(eng.stream)
+                ts_push.append((e0, e1))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(eng.stream)
             eng._enqueue_opt()
@@ -366,10 +386,12 @@ def kernel_breakdown(eng, flush, iters=20):
             ts.append(e0.elapsed_time(e1) * 1e3)
         for dst, src in zip((eng.params, eng.adam_m, eng.adam_v, eng.adam_step), keep):
             dst.copy_(src)
-        # read grad f64 + params/m/v read+write f32
-        # read grad f64 (from every rank when the kernel all-reduces over peer memory) + params/m/v rw
-        out["allreduce+clip_adam" if eng.peer else "clip_adam"] = dict(
+        # read grad f64 (world local slots when the gradient was pushed over peer memory) + params/m/v rw
+        out["gather+clip_adam" if pr else "clip_adam"] = dict(
             us=statistics.median(ts), flops=None, bytes=(8.0 * eng.world + 6 * 4.0) * eng.n_total)
+        if pr:
+            out["peer_push(stand-alone)"] = dict(us=statistics.median([a.elapsed_time(b) * 1e3 for a, b in ts_push]),
+                                                 flops=None, bytes=8.0 * eng.world * (eng.n_total + 8))
     eng.synchronize()
     return out
 
@@ -512,7 +534,7 @@ def run_own_arm(args):
 
     # ---------------- per-kernel roofline (rank 0 reports) ----------------
     with torch.cuda.stream(eng.stream):
-        kern = kernel_breakdown(eng, flush)
+        kern = kernel_breakdown(eng, flush, barrier=barrier)
     pk = peaks()
     fp32_peak = SMS * FP32_LANES * 2 * pk["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at max SM clock
     tf32_peak = pk["bf16_tflops"] / 2.0  # tf32 UMMA rate = half the (measured) bf16 rate
@@ -547,7 +569,7 @@ def run_own_arm(args):
                        frac=round(ach / pk["hbm_gbs"], 4))
         kernels[name] = ent
     in_step = ("mlp_forward_pair(policy+value_fn)", "vtrace_loss", "mlp_backward_pair(policy+value_fn)",
-               "allreduce+clip_adam" if eng.peer else "clip_adam")
+               "gather+clip_adam" if eng.peer else "clip_adam")
     for n in kernels:
         kernels[n]["in_step"] = n in in_step
     dom = max(in_step, key=lambda n: kernels[n]["us"])
@@ -610,7 +632,7 @@ def run_own_arm(args):
         vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=WORKLOAD_NAME, **w, global_batch=w["B"], per_gpu_batch=Bl,
                     parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step, "
-                                f"{'in the optimizer kernel over NVLink peer memory' if eng.peer else 'NCCL'})"
+                                f"{('pushed over NVLink peer memory from the ' + ('backward kernel tail' if eng.peer['fused'] else 'stand-alone producer kernel')) if eng.peer else 'NCCL'})"
                     if world > 1 else "single GPU",
                     l2="flushed between timed steps (256 MiB memset on the launching stream)",
                     cuda_graph=not args.no_graph, timing="sum of per-step CUDA-event intervals, max over ranks"),

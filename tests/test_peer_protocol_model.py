@@ -1,10 +1,13 @@
-"""CPU model of the handshake inside impala_allreduce_clip_adam (csrc/optim.cu).
+"""CPU model of the push all-reduce handshake (csrc/optim.cu, tail of csrc/mlp_bwd_tc.cu).
 
-The kernel's safety argument - parity-double-buffered contributions need only the "ready" flags, no
-acknowledgement round trip - is a protocol property, independent of CUDA: rank threads with random
-delays run it here and check that every read returns exactly the step it expects (never a buffer a
-fast peer has already overwritten, never a stale one).  The same model with ONE buffer per rank
-must fail, which shows the test can see the hazard the second buffer removes."""
+Protocol: the backward of step s on rank `me` STORES its contribution into slot `me` of parity
+s & 1 in EVERY rank's gather buffer, then posts flag[me] = s on every rank; the optimizer of step s
+waits until its own flag block shows s for all ranks, then reads its own `world` slots.  The
+safety argument - parity-double-buffered slots need only the "ready" flags, no acknowledgement
+round trip - is a protocol property, independent of CUDA: rank threads with random delays run it
+here and check that every read returns exactly the step it expects (never a slot a fast peer has
+already overwritten, never a stale one).  The same model with ONE buffer per rank must fail,
+which shows the test can see the hazard the second buffer removes."""
 import random
 import threading
 import time
@@ -13,7 +16,7 @@ import pytest
 
 
 def run_ranks(world: int, steps: int, buffers: int, seed: int):
-    contrib = [[0] * buffers for _ in range(world)]      # contrib[rank][parity] = step that wrote it
+    gather = [[[0] * world for _ in range(buffers)] for _ in range(world)]  # gather[owner][parity][writer] = step
     flags = [[0] * world for _ in range(world)]          # flags[owner][writer] = last step `writer` posted
     errors, stop = [], threading.Event()
 
@@ -22,18 +25,19 @@ def run_ranks(world: int, steps: int, buffers: int, seed: int):
         for s in range(1, steps + 1):
             if stop.is_set():
                 return
-            time.sleep(rng.random() * 2e-4)              # backward of step s ...
-            contrib[me][s % buffers] = s                 # ... leaves its gradient in buffer s & 1
-            for p in range(world):                       # optimizer kernel: post "ready"
+            time.sleep(rng.random() * 2e-4)              # forward / V-trace / backward of step s ...
+            for p in range(world):                       # ... whose tail pushes the gradient to everyone
+                gather[p][s % buffers][me] = s
+            for p in range(world):                       # last CTA out: release the flags
                 flags[p][me] = s
             t0 = time.time()
-            while any(flags[me][r] < s for r in range(world)):   # wait for every rank's flag
+            while any(flags[me][r] < s for r in range(world)):   # optimizer: wait on the LOCAL flag block
                 if stop.is_set() or time.time() - t0 > 20:
                     return
                 time.sleep(0)
             if rng.random() < 0.3:
                 time.sleep(rng.random() * 3e-4)          # a slow reader
-            got = [contrib[r][s % buffers] for r in range(world)]   # gather, rank order
+            got = list(gather[me][s % buffers])          # local slots, rank order
             if got != [s] * world:
                 errors.append((me, s, got))
                 stop.set()

@@ -78,3 +78,21 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
     for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(IMPALA_FULL_MASK, x, off);
     return x;
 }
+
+// ---- push-model all-reduce over peer memory (protocol: see optim.cu)
+struct PushArgs {
+    double* const* gather;     // device array [world]: every rank's gather buffer (peer-mapped)
+    long long* const* flags;   // device array [world]: every rank's flag block
+    const long long* seq;      // this rank's step counter (device, 1 word)
+    int64_t slot_stride;       // doubles between two ranks' slots
+    int64_t buf_stride;        // doubles between the two parity buffers
+    int rank, world;
+};
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}

@@ -472,18 +472,31 @@ __device__ __forceinline__ void grid_arrive_and_wait(unsigned int* ctl) {
     __syncthreads();
 }
 
-// The last CTA out re-arms the barrier for the next launch.
-__device__ __forceinline__ void grid_depart(unsigned int* ctl) {
-    if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
-        ctl[0] = 0u;
-        ctl[1] = 0u;
+// The last CTA out re-arms the barrier for the next launch.  With `push` (data-parallel learner,
+// see optim.cu): every CTA's peer stores are fenced at system scope before it counts itself out,
+// and the last CTA out then releases this rank's "step s contribution complete" flag on every rank.
+__device__ __forceinline__ void grid_depart(unsigned int* ctl, const PushArgs* push = nullptr) {
+    if (threadIdx.x == 0) {
+        if (push) __threadfence_system();
+        if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+            ctl[0] = 0u;
+            ctl[1] = 0u;
+            if (push) {
+                __threadfence_system();
+                const long long step = *push->seq + 1;
+                for (int r = 0; r < push->world; ++r) st_release_sys(push->flags[r] + push->rank, step);
+            }
+        }
     }
 }
 
 // Deterministic float64 sum of `nparts` partial rows: chunk c = entries [64c, 64c + 64); this CTA
 // takes chunks first, first + stride, ...; warp w adds rows w, w + kWarps, ... and warp 0 combines.
+// `push`: the sums go to entry push_off + e of slot `rank` in every rank's gather buffer instead of
+// a.grad (posted peer stores; the all-reduce of the data-parallel learner starts here).
 __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts, const int first,
-                                            const int stride, double* s_red) {
+                                            const int stride, double* s_red, const PushArgs* push = nullptr,
+                                            const int64_t push_off = 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total = a.lay.total;  // multiple of 32
     const int nchunks = (int)((total + 63) >> 6);
@@ -513,7 +526,14 @@ __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts
             double tx = 0.0, ty = 0.0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
-            *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
+            if (push) {
+                const int64_t off = ((*push->seq + 1) & 1) * push->buf_stride + (int64_t)push->rank * push->slot_stride +
+                                    push_off + e0;
+                for (int r = 0; r < push->world; ++r)
+                    *reinterpret_cast<double2*>(push->gather[r] + off) = make_double2(tx, ty);
+            } else {
+                *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
+            }
         }
         __syncthreads();
     }
@@ -542,9 +562,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(const __grid_co
 // tiles (partial rows 0 .. n_pi of its workspace), the rest the value function's.  After the grid
 // barrier every CTA helps reduce both sets of rows (the value function's chunks are dealt from
 // the far end so that no CTA gets two chunks of each).  Uses the policy workspace's control words.
+// PUSH: data-parallel learner - the reduced gradient [policy | value fn] and `n_extra` local
+// scalars (the loss sums the V-trace kernel left at `extra`) go straight into every rank's gather
+// buffer and the last CTA posts the flags (protocol in optim.cu); nothing is written to a.grad.
+template <bool PUSH>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_constant__ BwdTcArgs a_vf,
-                       const int n_pi) {
+                       const int n_pi, const __grid_constant__ PushArgs push, const double* extra,
+                       const int n_extra) {
     __shared__ long long s_trace[24 * 16];
     const int n_vf = (int)gridDim.x - n_pi;
     uint8_t* scratch;
@@ -552,9 +577,18 @@ mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_cons
     else scratch = bwd_tc_body<1>(a_vf, (int)blockIdx.x - n_pi, n_vf, s_trace);
     grid_arrive_and_wait(a_pi.ctl);
     const long long t_barrier = clock64();
-    reduce_rows(a_pi, n_pi, blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch));
-    reduce_rows(a_vf, n_vf, (int)gridDim.x - 1 - (int)blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch));
-    grid_depart(a_pi.ctl);
+    const PushArgs* pp = PUSH ? &push : nullptr;
+    reduce_rows(a_pi, n_pi, blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch), pp, 0);
+    reduce_rows(a_vf, n_vf, (int)gridDim.x - 1 - (int)blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch), pp,
+                a_pi.lay.total);
+    if (PUSH && blockIdx.x == gridDim.x / 2 && (int)threadIdx.x < n_extra) {
+        const int64_t off = ((*push.seq + 1) & 1) * push.buf_stride + (int64_t)push.rank * push.slot_stride +
+                            a_pi.lay.total + a_vf.lay.total + threadIdx.x;
+        const double val = extra[threadIdx.x];
+        for (int r = 0; r < push.world; ++r) push.gather[r][off] = val;
+    }
+    if (PUSH) __syncthreads();  // this CTA's peer stores precede thread 0's system fence
+    grid_depart(a_pi.ctl, pp);
     dump_trace(a_pi, s_trace, t_barrier);
 }
 
@@ -589,16 +623,17 @@ BwdTcArgs make_bwd_args(const float* x, const float* params, const float* dout, 
 int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, float* ws,
                       double* grad, unsigned int* ctl, int M, int O, int H, int N2, cudaStream_t st) {
     const BwdTcArgs a = make_bwd_args(x, params, dout, ws, grad, ctl, M, O, H, N2);
-    static bool opted[2] = {false, false};
+    static bool opted[64][2] = {};  // per device
     cudaError_t e;
-    int sms = 0;
+    int sms = 0, dev = 0;
     if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     const int which = N2 == 1 ? 0 : 1;
     auto kernel = which ? mlp_bwd_tc_kernel<4> : mlp_bwd_tc_kernel<1>;
-    if (!opted[which]) {
+    if (dev < 0 || dev >= 64 || !opted[dev][which]) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        opted[which] = true;
+        if (dev >= 0 && dev < 64) opted[dev][which] = true;
     }
     int grid = a.num_tiles < sms ? a.num_tiles : sms;  // <= SM count: the grid barrier needs residency
     if (grid > kMaxParts) grid = kMaxParts;
@@ -607,29 +642,35 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
 }
 
 // Both networks in one launch; the caller has checked eligibility of each and 2 <= A <= 4.
+// push != nullptr: data-parallel variant (see mlp_bwd_tc_pair_kernel).
 int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* params_vf,
                            const float* dlogits, const float* dv, float* ws_pi, float* ws_vf,
                            double* grad_pi, double* grad_vf, unsigned int* ctl, int M_pi, int M_vf, int O,
-                           int H_pi, int H_vf, int A, cudaStream_t st) {
+                           int H_pi, int H_vf, int A, cudaStream_t st, const PushArgs* push, const double* extra,
+                           int n_extra) {
     const BwdTcArgs a_pi = make_bwd_args(x, params_pi, dlogits, ws_pi, grad_pi, ctl, M_pi, O, H_pi, A);
     const BwdTcArgs a_vf = make_bwd_args(x, params_vf, dv, ws_vf, grad_vf, ctl, M_vf, O, H_vf, 1);
-    static bool opted = false;
+    static bool opted[64][2] = {};  // per device, per variant
     cudaError_t e;
-    int sms = 0;
+    int sms = 0, dev = 0;
     if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
-    if (!opted) {
-        e = cudaFuncSetAttribute(mlp_bwd_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kSmemBytes);
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    const int var = push ? 1 : 0;
+    if (dev < 0 || dev >= 64 || !opted[dev][var]) {
+        e = push ? cudaFuncSetAttribute(mlp_bwd_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)
+                 : cudaFuncSetAttribute(mlp_bwd_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        opted = true;
+        if (dev >= 0 && dev < 64) opted[dev][var] = true;
     }
     const int total_tiles = a_pi.num_tiles + a_vf.num_tiles;
     int grid = total_tiles < sms ? total_tiles : sms;
     if (grid > kMaxParts) grid = kMaxParts;
+    if (grid < 2) return IMPALA_ERR_UNSUPPORTED_SHAPE;
     const int n_pi = impala_pair_split(a_pi.num_tiles, a_vf.num_tiles, grid,
                                        impala_env_int("IMPALA_PAIR_W_BWD", 127) * (H_pi / 128),
                                        100 * (H_vf / 128));
-    mlp_bwd_tc_pair_kernel<<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi);
+    if (push) mlp_bwd_tc_pair_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi, *push, extra, n_extra);
+    else mlp_bwd_tc_pair_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi, PushArgs{}, nullptr, 0);
     return impala_launch_status();
 }
 

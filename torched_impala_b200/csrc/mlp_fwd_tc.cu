@@ -361,16 +361,17 @@ FwdTcArgs make_fwd_args(const float* x, const float* params, float* out, int M, 
 int impala_mlp_fwd_tc(const float* x, const float* params, float* out, int M, int O, int H, int N2,
                       cudaStream_t st) {
     const FwdTcArgs a = make_fwd_args(x, params, out, M, O, H, N2);
-    static bool opted[2] = {false, false};
+    static bool opted[64][2] = {};  // per device
     cudaError_t e;
-    int sms = 0;
+    int sms = 0, dev = 0;
     if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     const int which = N2 == 1 ? 0 : 1;
     auto kernel = which ? mlp_fwd_tc_kernel<4> : mlp_fwd_tc_kernel<1>;
-    if (!opted[which]) {
+    if (dev < 0 || dev >= 64 || !opted[dev][which]) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        opted[which] = true;
+        if (dev >= 0 && dev < 64) opted[dev][which] = true;
     }
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
@@ -385,15 +386,16 @@ int impala_mlp_fwd_tc_pair(const float* x, const float* params_pi, const float* 
                            cudaStream_t st) {
     const FwdTcArgs a_pi = make_fwd_args(x, params_pi, logits, M_pi, O, H_pi, A);
     const FwdTcArgs a_vf = make_fwd_args(x, params_vf, values, M_vf, O, H_vf, 1);
-    static bool opted = false;
+    static bool opted[64] = {};  // per device
     cudaError_t e;
-    int sms = 0;
+    int sms = 0, dev = 0;
     if ((e = impala_sm_count(&sms)) != cudaSuccess) return (int)e;
-    if (!opted) {
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
         e = cudaFuncSetAttribute(mlp_fwd_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        opted = true;
+        if (dev >= 0 && dev < 64) opted[dev] = true;
     }
     const int total_tiles = a_pi.num_tiles + a_vf.num_tiles;
     const int grid = total_tiles < sms ? total_tiles : sms;

@@ -47,7 +47,8 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
 int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* params_vf,
                            const float* dlogits, const float* dv, float* ws_pi, float* ws_vf,
                            double* grad_pi, double* grad_vf, unsigned int* ctl, int M_pi, int M_vf, int O,
-                           int H_pi, int H_vf, int A, cudaStream_t st);
+                           int H_pi, int H_vf, int A, cudaStream_t st, const PushArgs* push = nullptr,
+                           const double* extra = nullptr, int n_extra = 0);
 
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \

@@ -118,85 +118,112 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
 
 
 // ---------------------------------------------------------------------------------------------
-// Data-parallel learners: one-shot all-reduce over NVLink peer memory fused with clip + Adam.
+// Data-parallel learners: one-shot all-reduce over NVLink peer memory, PUSH model.
 //
-// Every rank leaves its float64 [gradient | extra scalars] contribution in a buffer that the other
-// ranks of the node have mapped (CUDA IPC).  Instead of an NCCL all-reduce between the backward
-// and the optimizer, the optimizer kernel of each rank
-//   1. posts "my contribution for step s is complete" into every peer's flag block,
-//   2. waits until all ranks' flags for step s have arrived in its own block,
-//   3. reads element i from all ranks (peer loads over NVLink / NVSwitch) and adds them in rank
-//      order - every rank forms bit-identical sums, so the replicas cannot drift,
-//   4. runs the clip norms and Adam on the sum.
-// The contribution buffers are double-buffered by step parity (buffer s & 1 for step s), which
-// makes a second "I have read your buffer" round trip unnecessary: a rank overwrites buffer s & 1
-// in the backward of step s + 2, i.e. after its optimizer kernel of step s + 1 saw every peer's
-// ready flag for s + 1 - and a peer posts that flag only after its kernel of step s (the one that
-// read the buffer) has finished.
-// Flags are monotonically increasing step numbers (int64, never reset); spins are bounded by a
-// clock timeout (~35 s) that traps (a lost rank becomes a launch failure on the others, not a hang).
-// Flag block of a rank: int64[world], entry r written by rank r.
-struct PeerArgs {
-    const double* const* contrib;  // device array [world]: every rank's 2 x [n_total + n_pad] doubles
-    int64_t buf_stride;            // doubles between the two parity buffers
-    long long* const* flags;       // device array [world]: every rank's flag block
-    long long* seq;                // this rank's step counter (device, 1 word)
-    int rank, world, n_extra;
-};
+// Every rank owns a gather buffer  G[2 parities][world slots][stride]  of float64 that the other
+// ranks of the node have mapped (CUDA IPC).  The producer of a rank's [gradient | extra scalars]
+// contribution - the reduction tail of the paired tensor-core backward kernel (mlp_bwd_tc.cu), or
+// peer_push_kernel below for shapes that kernel does not cover - STORES it into slot `rank` of every
+// rank's buffer (posted writes: nobody waits for an NVLink round trip), and the last CTA of that
+// producer then stores the step number into entry `rank` of every rank's flag block.  The
+// optimizer kernel of each rank waits until its OWN flag block shows this step for all ranks
+// (local polling), adds the `world` slots of its OWN buffer in rank order - every rank forms
+// bit-identical sums, so the replicas cannot drift - and runs the clip norms and Adam on the sum.
+//
+// Ordering: producer CTAs finish their peer stores, fence at system scope and count themselves
+// out on a device counter; the CTA that counts out last fences again and releases the flags
+// (st.release.sys).  Consumers acquire the flags (ld.acquire.sys) before touching the slots.
+// The buffers are double-buffered by step parity, which makes a second "I have read your slot"
+// round trip unnecessary: a rank overwrites parity s & 1 in the backward of step s + 2, i.e. after
+// its optimizer kernel of step s + 1 saw every peer's flag for s + 1 - and a peer posts that flag
+// only at the end of a backward that runs after its optimizer kernel of step s (the one that read
+// the slots) has finished.  The step number lives in device memory (`seq`, advanced by the
+// optimizer kernel), so both kernels derive the parity themselves and ONE captured CUDA graph
+// serves every step.
+//
+// A rank that never arrives (its host is stuck) does not kill the others' CUDA contexts: after
+// `timeout_ns` of polling the optimizer kernel sets an error word, leaves parameters, optimizer
+// state and `seq` untouched and exits normally; the host raises when it reads the word.
+// Flag block of a rank: int64[world], entry r written by rank r; monotonically increasing.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
-__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
-    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-    long long v;
-    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_peer_f64(const double* p) {  // not served from a local cache
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// lane r of the calling warp polls entry r of the block (all ranks in parallel), then the warp meets
-__device__ __forceinline__ void wait_flags(const long long* block, int n, long long seq, int lane) {
-    if (lane < n) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(block + lane) < seq)
-            if (clock64() - t0 > (1ll << 36)) __trap();  // ~35 s: a peer is gone
+constexpr int kPushCtas = 16, kPushThreads = 256;
+
+// Stand-alone producer: local[0, n) -> slot `rank` of every rank's gather buffer, then the flags.
+// ctl: one zeroed word (CTA count-out), re-armed by the last CTA.
+__global__ void __launch_bounds__(kPushThreads)
+peer_push_kernel(const double* __restrict__ local, int64_t n, PushArgs p, unsigned int* ctl) {
+    const long long step = *p.seq + 1;
+    const int64_t off = (step & 1) * p.buf_stride + (int64_t)p.rank * p.slot_stride;
+    const int64_t n2 = n >> 1;  // double2 granularity (n is padded to an even count by the caller)
+    for (int64_t i = (int64_t)blockIdx.x * kPushThreads + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kPushThreads) {
+        const double2 v = reinterpret_cast<const double2*>(local)[i];
+#pragma unroll 8
+        for (int r = 0; r < p.world; ++r) reinterpret_cast<double2*>(p.gather[r] + off)[i] = v;
     }
-    __syncwarp();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(ctl, 1u) == gridDim.x - 1) {
+            *ctl = 0u;
+            __threadfence_system();
+            for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + p.rank, step);
+        }
+    }
 }
 
+// Consumer: wait for every rank's flag, add the slots in rank order, clip + Adam.
 __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(kAdamThreads)
-allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced, PeerArgs peer,
-                           float* __restrict__ m, float* __restrict__ v, int64_t* __restrict__ state,
-                           int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
-                           float beta2, float eps, double* __restrict__ norms_out) {
+gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced,
+                        const double* __restrict__ gather, const long long* __restrict__ flags,
+                        long long* __restrict__ seq, int64_t slot_stride, int64_t buf_stride, int world,
+                        int n_extra, float* __restrict__ m, float* __restrict__ v,
+                        int64_t* __restrict__ state, int64_t n_policy, int64_t n_total, float max_norm,
+                        float lr, float beta1, float beta2, float eps, double* __restrict__ norms_out,
+                        int* __restrict__ err, unsigned long long timeout_ns) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double s_warp[2][kAdamThreads / 32];
     __shared__ double s_cta[2];
+    __shared__ int s_abort;     // this CTA gave up waiting (read by the peers of the cluster)
     __shared__ float s_coef[2];
     __shared__ float s_bias[2];
     __shared__ double s_pow[2];
-    __shared__ long long s_seq;
+    __shared__ long long s_step;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crank = (int)cluster.block_rank();
     const int64_t first = (int64_t)crank * kAdamThreads + tid;
     const int64_t stride = (int64_t)kAdamCluster * kAdamThreads;
-    long long* my_flags = peer.flags[peer.rank];
 
-    // 1. + 2.: post "ready" to everyone (one CTA, one lane per peer), then every CTA waits for all
-    // ranks' flags.  This rank's contribution was written by earlier kernels of the stream, i.e. it
-    // is already performed in its L2 (where peer reads are served); one system fence orders the
-    // flag stores behind it.
+    // optimizer state that does not depend on the peers: issued before the wait
+    constexpr int kKeep = 2, kMaxWorld = 8;  // one NVLink node
+    float pk[kKeep], mk[kKeep], vk[kKeep];
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int64_t i = first + k * stride;
+        pk[k] = i < n_total ? params[i] : 0.f;
+        mk[k] = i < n_total ? m[i] : 0.f;
+        vk[k] = i < n_total ? v[i] : 0.f;
+    }
     if (warp == 0) {
-        const long long seq = *peer.seq + 1;
-        if (lane == 0) s_seq = seq;
-        if (crank == 0) {
-            __threadfence_system();
-            if (lane < peer.world) st_relaxed_sys(peer.flags[lane] + peer.rank, seq);
+        const long long step = *seq + 1;
+        int gave_up = 0;
+        if (lane < world) {  // lane r polls rank r's entry of the local flag block
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (ld_acquire_sys(flags + lane) < step) {
+                if ((++spins & 63u) == 0 && global_ns() - t0 > timeout_ns) {
+                    gave_up = 1;
+                    break;
+                }
+                __nanosleep(32);
+            }
         }
-        wait_flags(my_flags, peer.world, seq, lane);
+        gave_up = __any_sync(IMPALA_FULL_MASK, gave_up);
+        if (lane == 0) s_step = step, s_abort = gave_up;
     }
     if (tid == 64) {  // bias corrections from the running powers (nobody writes state before the end)
         const double p1 = state[0] == 0 ? 1.0 : __longlong_as_double(state[1]);
@@ -207,41 +234,39 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
     }
     __syncthreads();
 
-    // 3. rank-ordered sums of this thread's entries (all loads of an entry are independent)
-    constexpr int kKeep = 2, kMaxWorld = 8;  // one NVLink node
-    const int64_t boff = (s_seq & 1) * peer.buf_stride;  // this step's parity buffer
-    auto gather = [&](int64_t i) {
+    // rank-ordered sums of this thread's entries: all local loads, independent of each other
+    const double* gb = gather + (s_step & 1) * buf_stride;
+    auto gsum = [&](int64_t i) {
         double c[kMaxWorld];
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < peer.world) c[r] = ld_peer_f64(peer.contrib[r] + boff + i);
+            if (r < world) c[r] = __ldcg(gb + r * slot_stride + i);
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < peer.world) s += c[r];
+            if (r < world) s += c[r];
         return s;
     };
     double gk[kKeep];
-    float pk[kKeep], mk[kKeep], vk[kKeep];
     double ss0 = 0.0, ss1 = 0.0;
+    const bool go = !s_abort;
 #pragma unroll
     for (int k = 0; k < kKeep; ++k) {
         const int64_t i = first + k * stride;
-        gk[k] = i < n_total ? gather(i) : 0.0;
-        pk[k] = i < n_total ? params[i] : 0.f;
-        mk[k] = i < n_total ? m[i] : 0.f;
-        vk[k] = i < n_total ? v[i] : 0.f;
-        if (i < n_total) reduced[i] = gk[k];
+        gk[k] = (go && i < n_total) ? gsum(i) : 0.0;
+        if (go && i < n_total) reduced[i] = gk[k];
         if (i < n_policy) ss0 += gk[k] * gk[k];
         else ss1 += gk[k] * gk[k];
     }
-    for (int64_t i = first + kKeep * stride; i < n_total; i += stride) {
-        const double g = gather(i);
-        reduced[i] = g;
-        if (i < n_policy) ss0 += g * g;
-        else ss1 += g * g;
+    if (go) {
+        for (int64_t i = first + kKeep * stride; i < n_total; i += stride) {
+            const double g = gsum(i);
+            reduced[i] = g;
+            if (i < n_policy) ss0 += g * g;
+            else ss1 += g * g;
+        }
+        if (crank == 0 && tid < n_extra) reduced[n_total + tid] = gsum(n_total + tid);  // logged scalars
     }
-    if (crank == 0 && tid < peer.n_extra) reduced[n_total + tid] = gather(n_total + tid);  // logged scalars
     ss0 = warp_sum_f64(ss0);
     ss1 = warp_sum_f64(ss1);
     if (lane == 0) s_warp[0][warp] = ss0, s_warp[1][warp] = ss1;
@@ -251,7 +276,13 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
         for (int i = 0; i < kAdamThreads / 32; ++i) s += s_warp[tid][i];
         s_cta[tid] = s;
     }
-    cluster.sync();  // all 8 partial pairs are in place; every CTA has finished its peer reads
+    cluster.sync();  // all 8 partial pairs (and abort flags) are in place
+    __shared__ int s_any_abort;
+    if (tid == 0) {
+        int ab = 0;
+        for (int r = 0; r < kAdamCluster; ++r) ab |= *cluster.map_shared_rank(&s_abort, r);
+        s_any_abort = ab;
+    }
     if (tid < 2) {
         double s = 0.0;
         for (int r = 0; r < kAdamCluster; ++r) s += *cluster.map_shared_rank(&s_cta[tid], r);
@@ -260,31 +291,37 @@ allreduce_clip_adam_kernel(float* __restrict__ params, double* __restrict__ redu
         if (norms_out && crank == 0) norms_out[tid] = norm;
     }
     __syncthreads();
-    const float b1 = beta1, b2 = beta2, step_size = s_bias[0], inv_bc2_sqrt = s_bias[1];
-    const float c0 = s_coef[0], c1 = s_coef[1];
-    auto update = [&](int64_t i, float g, float p, float mi, float vi) {
-        g *= (i < n_policy ? c0 : c1);
-        mi = fmaf(b1, mi, (1.f - b1) * g);
-        vi = fmaf(b2, vi, (1.f - b2) * g * g);
-        const float denom = fmaf(sqrtf(vi), inv_bc2_sqrt, eps);
-        params[i] = p - step_size * mi / denom;
-        m[i] = mi;
-        v[i] = vi;
-    };
+    if (!s_any_abort) {
+        const float b1 = beta1, b2 = beta2, step_size = s_bias[0], inv_bc2_sqrt = s_bias[1];
+        const float c0 = s_coef[0], c1 = s_coef[1];
+        auto update = [&](int64_t i, float g, float p, float mi, float vi) {
+            g *= (i < n_policy ? c0 : c1);
+            mi = fmaf(b1, mi, (1.f - b1) * g);
+            vi = fmaf(b2, vi, (1.f - b2) * g * g);
+            const float denom = fmaf(sqrtf(vi), inv_bc2_sqrt, eps);
+            params[i] = p - step_size * mi / denom;
+            m[i] = mi;
+            v[i] = vi;
+        };
 #pragma unroll
-    for (int k = 0; k < kKeep; ++k) {
-        const int64_t i = first + k * stride;
-        if (i < n_total) update(i, (float)gk[k], pk[k], mk[k], vk[k]);
+        for (int k = 0; k < kKeep; ++k) {
+            const int64_t i = first + k * stride;
+            if (i < n_total) update(i, (float)gk[k], pk[k], mk[k], vk[k]);
+        }
+        for (int64_t i = first + kKeep * stride; i < n_total; i += stride)
+            update(i, (float)reduced[i], params[i], m[i], v[i]);
     }
-    for (int64_t i = first + kKeep * stride; i < n_total; i += stride)
-        update(i, (float)reduced[i], params[i], m[i], v[i]);
     cluster.sync();  // peers finished reading this CTA's shared memory; every CTA has read state
     if (crank == 0 && tid == 64) {
-        state[0] += 1;
-        state[1] = __double_as_longlong(s_pow[0]);
-        state[2] = __double_as_longlong(s_pow[1]);
+        if (s_any_abort) {
+            if (err) *err = 1;  // the host raises; state and seq stay as they were
+        } else {
+            state[0] += 1;
+            state[1] = __double_as_longlong(s_pow[0]);
+            state[2] = __double_as_longlong(s_pow[1]);
+            *seq = s_step;
+        }
     }
-    if (crank == 0 && tid == 0) *peer.seq = s_seq;
 }
 
 }  // namespace
@@ -300,19 +337,32 @@ extern "C" int impala_clip_adam(float* params, const double* grad, float* m, flo
     return impala_launch_status();
 }
 
-extern "C" int impala_allreduce_clip_adam(float* params, double* reduced, const double* const* peer_contrib,
-                                          int64_t buf_stride, long long* const* peer_flags, long long* seq,
-                                          int rank, int world, int n_extra, float* m, float* v, int64_t* state, int64_t n_policy,
-                                          int64_t n_total, float max_norm, float lr, float beta1, float beta2,
-                                          float eps, double* norms_out, void* stream) {
-    if (!params || !reduced || !peer_contrib || !peer_flags || !seq || !m || !v || !state)
-        return IMPALA_ERR_BAD_ARG;
+extern "C" int impala_peer_push(const double* local, int64_t n, double* const* peer_gather,
+                                long long* const* peer_flags, const long long* seq, int64_t slot_stride,
+                                int64_t buf_stride, int rank, int world, unsigned int* ctl, void* stream) {
+    if (!local || !peer_gather || !peer_flags || !seq || !ctl) return IMPALA_ERR_BAD_ARG;
+    if (n < 2 || (n & 1) || world < 1 || world > 8 || rank < 0 || rank >= world) return IMPALA_ERR_BAD_ARG;
+    if (slot_stride < n || (slot_stride & 1) || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(local) & 15) != 0) return IMPALA_ERR_BAD_ARG;
+    PushArgs p{peer_gather, peer_flags, seq, slot_stride, buf_stride, rank, world};
+    peer_push_kernel<<<kPushCtas, kPushThreads, 0, (cudaStream_t)stream>>>(local, n, p, ctl);
+    return impala_launch_status();
+}
+
+extern "C" int impala_gather_clip_adam(float* params, double* reduced, const double* gather,
+                                       const long long* flags, long long* seq, int64_t slot_stride,
+                                       int64_t buf_stride, int world, int n_extra, float* m, float* v,
+                                       int64_t* state, int64_t n_policy, int64_t n_total, float max_norm,
+                                       float lr, float beta1, float beta2, float eps, double* norms_out,
+                                       int* err, double timeout_s, void* stream) {
+    if (!params || !reduced || !gather || !flags || !seq || !m || !v || !state) return IMPALA_ERR_BAD_ARG;
     if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
-    if (world < 1 || world > 8 || rank < 0 || rank >= world || n_extra < 0 || n_extra > kAdamThreads)
-        return IMPALA_ERR_BAD_ARG;
-    if (buf_stride < n_total + n_extra) return IMPALA_ERR_BAD_ARG;
-    PeerArgs peer{peer_contrib, buf_stride, peer_flags, seq, rank, world, n_extra};
-    allreduce_clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
-        params, reduced, peer, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
+    if (world < 1 || world > 8 || n_extra < 0 || n_extra > kAdamThreads) return IMPALA_ERR_BAD_ARG;
+    if (slot_stride < n_total + n_extra || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
+    const unsigned long long timeout_ns =
+        timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 600ull * 1000000000ull;
+    gather_clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
+        params, reduced, gather, flags, seq, slot_stride, buf_stride, world, n_extra, m, v, state, n_policy,
+        n_total, max_norm, lr, beta1, beta2, eps, norms_out, err, timeout_ns);
     return impala_launch_status();
 }

@@ -10,12 +10,15 @@ include/impala_b200.h (PyTorch only provides device memory, streams and
     impala_vtrace_loss         V-trace, 3 losses, dL/dlogits, dL/dv, scalars    learner.py:116-162
     impala_mlp_backward_pair   parameter gradients of both nets (float64)       learner.py:175
     impala_clip_adam           per-net clip + Adam + step counter               learner.py:176-183
-      N > 1: impala_allreduce_clip_adam - the same kernel first sums [grads | scalars] of all
-      ranks over NVLink peer memory (new).  IMPALA_ALLREDUCE=nccl: torch.distributed
-      all-reduce between the backward and impala_clip_adam instead.
+      N > 1 (new): the all-reduce of [grads | scalars] is a PUSH over NVLink peer memory -
+      the tail of impala_mlp_backward_pair_push (or impala_peer_push for shapes it does not cover)
+      stores this rank's contribution into every rank's gather buffer and posts a flag;
+      impala_gather_clip_adam waits for the local flags, adds the local slots in rank order and
+      applies the update.  IMPALA_ALLREDUCE=nccl: torch.distributed all-reduce between the
+      backward and impala_clip_adam instead.
 
-With `use_graph=True` the whole launch sequence of a step is captured once per (slab, parity
-buffer) into ONE CUDA graph and replayed (two graphs around the collective in the NCCL scheme).
+With `use_graph=True` the whole launch sequence of a step is captured once per slab into ONE CUDA
+graph and replayed (two graphs around the collective in the NCCL scheme).
 Ingest is double buffered: two pinned host slabs, two device slabs and
 a dedicated copy stream, so the DMA of batch i+1 runs under the kernels of batch i
 (`ingest(slot)` / `step(slot)` order themselves with events); the loss scalars come back
@@ -125,7 +128,7 @@ class LearnerEngine:
         self._scalar_events = [torch.cuda.Event() for _ in range(4)]
         self._ticket = 0
 
-        self._graph_main = {}  # (slab slot, contribution-buffer parity) -> captured step
+        self._graph_main = {}  # slab slot -> captured step
         self._graph_opt = None
         self._main_launches = 0
         self.steps_done = 0
@@ -136,9 +139,9 @@ class LearnerEngine:
     # ------------------------------------------------------------------ parameters
     # ------------------------------------------------------------------------ multi-GPU plumbing
     def _setup_peer_allreduce(self) -> None:
-        """Map every rank's contribution buffer and flag block (CUDA IPC over NVLink) for
-        impala_allreduce_clip_adam.  IMPALA_ALLREDUCE=nccl - or a failed mapping on ANY rank - keeps
-        the torch.distributed all-reduce between the backward and the optimizer instead."""
+        """Allocate this rank's gather buffer and flag block, map every peer's (CUDA IPC over NVLink)
+        for the push-model all-reduce.  IMPALA_ALLREDUCE=nccl - or a failed mapping on ANY rank -
+        keeps the torch.distributed all-reduce between the backward and the optimizer instead."""
         import os
         import warnings
 
@@ -146,10 +149,12 @@ class LearnerEngine:
 
         rank, world = dist.get_rank(self.pg), self.world
         ok, err, mine = os.environ.get("IMPALA_ALLREDUCE", "peer") != "nccl" and world <= 8, "", {}
-        n_doubles, lib = self.n_total + 8, self.lib
+        lib = self.lib
+        slot = (self.n_total + 8 + 1) // 2 * 2          # doubles per rank slot: [gradient | scalars | pad], even
+        buf = world * slot                              # doubles per parity buffer
         if ok:
-            try:  # two parity buffers of [gradient | scalars | pad]; one ready flag per rank
-                for name, nbytes in (("contrib", 2 * 8 * n_doubles), ("flags", 8 * world)):
+            try:
+                for name, nbytes in (("gather", 2 * 8 * buf), ("flags", 8 * world)):
                     ptr, handle = C.c_void_p(), (C.c_char * 64)()
                     _cabi.check(lib.impala_peer_alloc(nbytes, C.byref(ptr), handle), "impala_peer_alloc")
                     mine[name] = (ptr.value, bytes(handle.raw))
@@ -158,12 +163,12 @@ class LearnerEngine:
         handles = [None] * world
         dist.all_gather_object(handles, {k: v[1] for k, v in mine.items()} if ok else None, group=self.pg)
         ok = ok and all(h is not None for h in handles)
-        ptrs = {"contrib": [], "flags": []}
+        ptrs = {"gather": [], "flags": []}
         opened = []
         if ok:
             try:
                 for r, h in enumerate(handles):
-                    for name in ("contrib", "flags"):
+                    for name in ("gather", "flags"):
                         if r == rank:
                             ptrs[name].append(mine[name][0])
                         else:
@@ -181,9 +186,15 @@ class LearnerEngine:
                               "using the NCCL all-reduce between backward and optimizer")
             return
         i64 = dict(dtype=torch.int64, device=self.dev)
-        self.peer = dict(contrib=mine["contrib"][0], flags=mine["flags"][0], opened=opened,
-                         contrib_ptrs=torch.tensor(ptrs["contrib"], **i64), flag_ptrs=torch.tensor(ptrs["flags"], **i64),
-                         seq=torch.zeros(1, **i64), rank=rank, stride=n_doubles, calls=0)
+        fused = bool(lib.impala_mlp_backward_pair_push_supported(self.M_pi, self.M_vf, self.O, self.H_pi, self.H_v, self.A))
+        if os.environ.get("IMPALA_PUSH_FUSED", "1") == "0":
+            fused = False
+        self.peer = dict(gather=mine["gather"][0], flags=mine["flags"][0], opened=opened,
+                         gather_ptrs=torch.tensor(ptrs["gather"], **i64), flag_ptrs=torch.tensor(ptrs["flags"], **i64),
+                         seq=torch.zeros(1, **i64), rank=rank, slot=slot, buf=buf, fused=fused,
+                         ctl=torch.zeros(4, dtype=torch.int32, device=self.dev),
+                         err=torch.zeros(1, dtype=torch.int32, device=self.dev),
+                         timeout_s=float(os.environ.get("IMPALA_PEER_TIMEOUT_S", "600")))
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=self.pg)
 
@@ -285,11 +296,10 @@ class LearnerEngine:
         T, B, O, A = self.T, self.B, self.O, self.A
         p_pi = C.c_void_p(self.params.data_ptr())
         p_vf = C.c_void_p(self.params.data_ptr() + 4 * self.n_pi)
-        # this rank's [gradient | scalars]: the peer-mapped contribution buffer when the optimizer
-        # kernel does the all-reduce itself, else `comm` (reduced in place by NCCL, or final at N=1)
-        # (parity buffer (k + 1) & 1 for the k-th optimizer call, see impala_allreduce_clip_adam)
-        gbase = (self.peer["contrib"] + 8 * self.peer["stride"] * ((self.peer["calls"] + 1) & 1) if self.peer
-                 else self.comm.data_ptr())
+        # this rank's [gradient | scalars] goes to `comm` (final at N = 1, reduced in place by NCCL,
+        # source of impala_peer_push); the fused push variant of the backward sends the gradient
+        # straight to the peers and only the scalars pass through `comm`
+        gbase = self.comm.data_ptr()
         g_pi = C.c_void_p(gbase)
         g_vf = C.c_void_p(gbase + 8 * self.n_pi)
         scal = C.c_void_p(gbase + 8 * self.n_total)
@@ -305,23 +315,33 @@ class LearnerEngine:
             float(hp.gamma), float(hp.rho_bar), float(hp.c_bar), float(hp.v_loss_c),
             float(hp.policy_loss_c), float(hp.entropy_c), float(self.inv_batch), self.mode, st),
             "impala_vtrace_loss")
-        _cabi.check(lib.impala_mlp_backward_pair(
-            obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), g_pi, g_vf, _ptr(self.ws_pi), self.ws_pi_bytes,
-            _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
-            "impala_mlp_backward_pair")
+        pr = self.peer
+        if pr and pr["fused"]:
+            _cabi.check(lib.impala_mlp_backward_pair_push(
+                obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), _ptr(self.ws_pi), self.ws_pi_bytes,
+                _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, scal, 4,
+                _ptr(pr["gather_ptrs"]), _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"],
+                self.world, st), "impala_mlp_backward_pair_push")
+        else:
+            _cabi.check(lib.impala_mlp_backward_pair(
+                obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), g_pi, g_vf, _ptr(self.ws_pi), self.ws_pi_bytes,
+                _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
+                "impala_mlp_backward_pair")
+            if pr:  # stand-alone producer: comm[0 : n_total + 8) -> every rank's gather buffer, then the flags
+                _cabi.check(lib.impala_peer_push(_ptr(self.comm), self.n_total + 8, _ptr(pr["gather_ptrs"]),
+                                                 _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"],
+                                                 pr["rank"], self.world, _ptr(pr["ctl"]), st), "impala_peer_push")
         return int(lib.impala_launch_count() - launched)  # kernels actually launched / captured
 
     def _enqueue_opt(self) -> int:
         hp, st = self.hp, C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.peer:
             pr = self.peer
-            _cabi.check(self.lib.impala_allreduce_clip_adam(
-                _ptr(self.params), _ptr(self.comm), _ptr(pr["contrib_ptrs"]), pr["stride"], _ptr(pr["flag_ptrs"]),
-                _ptr(pr["seq"]), pr["rank"], self.world, 4, _ptr(self.adam_m), _ptr(self.adam_v),
-                _ptr(self.adam_step), self.n_pi, self.n_total, float(hp.max_norm), float(0.95 * hp.lr),
-                0.9, 0.999, 1e-8, _ptr(self.norms), st), "impala_allreduce_clip_adam")
-            if not torch.cuda.is_current_stream_capturing():
-                pr["calls"] += 1  # mirrors the device-side call counter (selects the parity buffer)
+            _cabi.check(self.lib.impala_gather_clip_adam(
+                _ptr(self.params), _ptr(self.comm), C.c_void_p(pr["gather"]), C.c_void_p(pr["flags"]), _ptr(pr["seq"]),
+                pr["slot"], pr["buf"], self.world, 4, _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.adam_step),
+                self.n_pi, self.n_total, float(hp.max_norm), float(0.95 * hp.lr), 0.9, 0.999, 1e-8,
+                _ptr(self.norms), _ptr(pr["err"]), pr["timeout_s"], st), "impala_gather_clip_adam")
             return 1
         _cabi.check(self.lib.impala_clip_adam(
             _ptr(self.params), _ptr(self.comm), _ptr(self.adam_m), _ptr(self.adam_v),
@@ -337,19 +357,15 @@ class LearnerEngine:
                 self._main_launches = self._enqueue_main(slot)
                 if self._one_graph():  # no library collective in between: the optimizer joins the graph
                     self._enqueue_opt()
-            self._graph_main[(slot, self._parity())] = g1
+            self._graph_main[slot] = g1
             if not self._one_graph() and self._graph_opt is None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, stream=self.stream):
                     self._enqueue_opt()
                 self._graph_opt = g2
 
-    def _parity(self) -> int:
-        """Which of this rank's two contribution buffers the next step writes (0 without peers)."""
-        return (self.peer["calls"] + 1) & 1 if self.peer else 0
-
     def _one_graph(self) -> bool:
-        """Single GPU, or the optimizer kernel all-reduces over peer memory itself."""
+        """Single GPU, or the all-reduce is the push over peer memory (no library call in between)."""
         return self.world == 1 or self.peer is not None
 
     def step(self, slot: int = 0) -> None:
@@ -357,14 +373,11 @@ class LearnerEngine:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.slab_ready[slot])
             if self.use_graph and self.steps_done >= 1:
-                key = (slot, self._parity())
-                if key not in self._graph_main:
+                if slot not in self._graph_main:
                     self._capture(slot)
-                self._graph_main[key].replay()
+                self._graph_main[slot].replay()
                 n = self._main_launches
                 fused_opt = self._one_graph()
-                if self.peer:
-                    self.peer["calls"] += 1  # the replayed graph ran impala_allreduce_clip_adam
             else:
                 n = self._enqueue_main(slot)  # first step eager: fills the launch-config caches
                 fused_opt = False
@@ -401,12 +414,18 @@ class LearnerEngine:
         with torch.cuda.stream(self.stream):
             self.h_scalars[k, :4].copy_(self.comm[self.n_total:self.n_total + 4], non_blocking=True)
             self.h_scalars[k, 4:6].copy_(self.norms, non_blocking=True)
+            if self.peer:
+                self.h_scalars[k, 6:7].copy_(self.peer["err"].to(torch.float64), non_blocking=True)
             self._scalar_events[k].record(self.stream)
         return k
 
     def fetch_scalars(self, ticket: int) -> dict:
         self._scalar_events[ticket].synchronize()
         s = self.h_scalars[ticket].tolist()
+        if self.peer and s[6] != 0.0:
+            raise _cabi.ImpalaCudaError(
+                f"data-parallel learner: a peer rank did not deliver its gradient within {self.peer['timeout_s']:.0f} s "
+                "(IMPALA_PEER_TIMEOUT_S); parameters were left untouched on this rank")
         hp = self.hp
         out = dict(zip(SCALAR_NAMES, s[:4]))
         out["total_loss"] = (hp.v_loss_c * out["value_fn_loss"] + hp.policy_loss_c * out["policy_loss"]
