@@ -66,6 +66,13 @@ int impala_batch_layout(int T, int B, int O, int A, int64_t offsets[6], int64_t*
 /* Host slab -> device slab, async on `stream` (host memory should be pinned). */
 int impala_ingest(void* dev_slab, const void* host_slab, int64_t bytes, void* stream);
 
+/* Data-parallel ingest: copy columns [b0, b0 + B_local) of a host slab laid out by
+ * impala_batch_layout(T, B, O, A) into a device slab laid out by impala_batch_layout(T, B_local, O, A)
+ * (strided 2-D DMAs; the host slab should be page-locked).  Every rank of a data-parallel learner
+ * pulls its own shard of the actors' shared-memory slab over its own PCIe link. */
+int impala_ingest_shard(void* dev_slab, const void* host_slab, int T, int B, int O, int A, int b0,
+                        int B_local, void* stream);
+
 /* out[m, :] = relu(x[m, :] W1^T + b1) W2^T + b2 for m < M.
  * Replaces MlpPolicy.forward / MlpValueFn.forward in eval mode
  * (models.py:23-25, :51-52) as called at learner.py:112-113 on the flattened

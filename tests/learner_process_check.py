@@ -43,7 +43,9 @@ def main():
         q = mp.Queue(maxsize=hp.queue_lim)
     counter = Counter(0)
     log_dir = sys.argv[1] if len(sys.argv) > 1 else None
-    lrn = Learner(1, hp, policy, value_fn, q, counter, log_path=log_dir, timeout=60)
+    n_dev = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # > 1: data-parallel learner (dp.py), still ONE Learner
+    lrn = Learner(1, hp, policy, value_fn, q, counter, log_path=log_dir, timeout=60,
+                  devices=[f"cuda:{i}" for i in range(n_dev)])
 
     def feed():  # stands in for actor processes: same wire format, same bounded queue
         for u in range(g.updates):
@@ -71,7 +73,9 @@ def main():
         assert set(torch.load(ck)) == {"policy_state_dict", "value_fn_state_dict"}
     if use_ring:
         q.close()
-    print(f"LEARNER_PROCESS_OK updates={counter.value} max|dW|={worst:.2e} ring={use_ring}")
+    assert lrn.policy_version >= 2 * g.updates, lrn.policy_version  # one publication per update + the final sync
+    print(f"LEARNER_PROCESS_OK updates={counter.value} max|dW|={worst:.2e} ring={use_ring} devices={n_dev} "
+          f"version={lrn.policy_version}")
 
 
 if __name__ == "__main__":

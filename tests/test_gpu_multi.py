@@ -26,3 +26,17 @@ def test_two_rank_learner_matches_single_gpu(allreduce):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout
     assert f"allreduce={allreduce}" in res.stdout  # the requested path is the one that ran
+
+
+@pytest.mark.parametrize("transport", ["queue", "ring"])
+def test_dp_learner_process_two_gpus(tmp_path, transport):
+    """SURVEY 8e through the PRODUCT API: one forked `Learner(devices=[cuda:0, cuda:1])` behind the
+    real queue / ring, worker rank spawned by it, shards DMA'd per rank, weights compared with the
+    real reference's (golden c1)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(__file__), "learner_process_check.py")
+    res = subprocess.run([sys.executable, script, str(tmp_path / "logs"), transport, "2"], capture_output=True,
+                         text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "LEARNER_PROCESS_OK" in res.stdout and "devices=2" in res.stdout

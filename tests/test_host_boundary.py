@@ -162,3 +162,42 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[0] == "1" and out[1] == "0"
     assert int(out[2]) == _cabi.param_layout(24, 256, 4)[1]
+
+
+def test_policy_snapshot_is_versioned():
+    """publications bump a shared version (odd while a write is in progress) and
+    policy_snapshot() never returns a torn copy; policy_weights keeps the reference's semantics."""
+    hp = default_hparams(batch_size=2, max_timesteps=5, max_updates=1)
+    policy, value_fn = MlpPolicy(4, 2, 8), MlpValueFn(4, 8)
+    policy.share_memory()
+    lrn = Learner(1, hp, policy, value_fn, queue.Queue(), Counter(0))
+    assert lrn.policy_version == 0
+    v, sd = lrn.policy_snapshot()
+    assert v == 0 and set(sd) == set(PKEYS)
+    assert all(torch.equal(sd[k], policy.state_dict()[k]) and sd[k] is not policy.state_dict()[k] for k in PKEYS)
+    lrn._version.value += 2  # what a completed publication does
+    assert lrn.policy_version == 2 and lrn.policy_snapshot()[0] == 2
+
+
+def test_shard_control_block_and_dp_config():
+    """Host side of the data-parallel learner: control block shared by name, JSON-able config."""
+    import json
+
+    from torched_impala_b200 import dp
+
+    ctl = dp.ShardControl()
+    try:
+        other = dp.ShardControl(ctl.name)
+        ctl.w[dp._CMD] = 7
+        ctl.w[dp._DMA_ACK + 3] = 5
+        assert other.w[dp._CMD] == 7 and other.w[dp._DMA_ACK + 3] == 5 and other.w[dp._STOP] == 0
+        other.close()
+    finally:
+        ctl.close()
+    hp = default_hparams(batch_size=4, max_timesteps=5, log_path=None)
+    lrn = Learner(2, hp, MlpPolicy(4, 2, 8), MlpValueFn(4, 8), queue.Queue(), Counter(0), devices=["cuda:0", "cuda:1"])
+    cfg = lrn._cfg()
+    assert json.loads(json.dumps(cfg))["B"] == 4 and cfg["H_pi"] == 8 and lrn.devices == ["cuda:0", "cuda:1"]
+    with pytest.raises(ValueError):
+        Learner(3, default_hparams(batch_size=3), MlpPolicy(4, 2, 8), MlpValueFn(4, 8), queue.Queue(), Counter(0),
+                devices=["cuda:0", "cuda:1"])._make_engine(None, 2)

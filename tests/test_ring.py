@@ -118,3 +118,71 @@ def test_layout_matches_c_abi():
 
     for shape in ((20, 4096, 24, 4), (10, 8, 5, 3), (1000, 32, 4, 2)):
         assert _layout(*shape) == tuple(_cabi.batch_layout(*shape))
+
+
+def test_malformed_trajectory_never_leaves_a_hole():
+    """a bad trajectory must be rejected BEFORE a column is taken, so the batch still
+    completes with the good ones (mp.Queue had no such failure mode)."""
+    ring = RingQueue(T, 2, O, A, slabs=2)
+    try:
+        trajs = synth.to_trajectories(synth.make_batch(1, T, 3, O, A))
+        bad = synth.to_trajectories(synth.make_batch(2, T + 4, 1, O, A))[0]  # longer than the unroll
+        ring.put(trajs[0], timeout=1)
+        with pytest.raises(ValueError):
+            ring.put(bad, timeout=1)
+        trajs[1].obs.pop()  # malformed lists
+        with pytest.raises(ValueError):
+            ring.put(trajs[1], timeout=1)
+        ring.put(trajs[2], timeout=1)
+        k, _ = ring.collect_batch(timeout=1)  # two good trajectories fill the two columns
+        assert ring.views(k)["lens"].tolist() == [T, T]
+    finally:
+        ring.close()
+
+
+def _block_writer(ring, wid, blocks, n):
+    for i in range(blocks):
+        blk = synth.make_batch(100 * wid + i, T, n, O, A, ragged=True)
+        while True:
+            try:
+                ring.put_block(blk, timeout=0.05)
+                break
+            except queue.Full:
+                continue
+
+
+def test_put_block_from_two_processes():
+    """Pre-stacked payload: blocks of n columns, two writer processes, every block
+    lands intact in n consecutive columns and the reward sum matches."""
+    ctx = mp.get_context("fork")
+    Bs, n, blocks = 8, 4, 6
+    ring = RingQueue(T, Bs, O, A, slabs=2)
+    try:
+        ps = [ctx.Process(target=_block_writer, args=(ring, w, blocks, n)) for w in range(2)]
+        for p in ps:
+            p.start()
+        want = {(w, i): synth.make_batch(100 * w + i, T, n, O, A, ragged=True) for w in range(2) for i in range(blocks)}
+        seen = 0
+        for _ in range(2 * blocks * n // Bs):
+            k, reward = ring.collect_batch(timeout=30)
+            v = ring.views(k)
+            total = 0.0
+            for b0 in range(0, Bs, n):
+                hit = [key for key, blk in want.items() if np.array_equal(v["obs"][:, b0:b0 + n], blk["obs"])]
+                assert len(hit) == 1
+                blk = want.pop(hit[0])
+                for name in ("beh_logits", "actions", "rewards", "done"):
+                    np.testing.assert_array_equal(v[name][:, b0:b0 + n], blk[name])
+                np.testing.assert_array_equal(v["lens"][b0:b0 + n], blk["lens"])
+                total += float(blk["rewards"].astype(np.float64).sum())
+                seen += 1
+            assert abs(reward - total / Bs) < 1e-9
+            ring.release(k)
+        assert seen == 2 * blocks and not want
+        for p in ps:
+            p.join(timeout=10)
+            assert p.exitcode == 0
+        with pytest.raises(ValueError):
+            ring.put_block(synth.make_batch(0, T, 3, O, A))  # 3 does not divide 8
+    finally:
+        ring.close()

@@ -30,6 +30,7 @@ SIGNATURES = {
     "impala_param_layout": (_i, [_i, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "impala_batch_layout": (_i, [_i, _i, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "impala_ingest": (_i, [_p, _p, _i64, _p]),
+    "impala_ingest_shard": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "impala_mlp_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "impala_launch_count": (C.c_longlong, []),
     "impala_mlp_forward_pair": (_i, [_p] * 5 + [_i] * 6 + [_p]),

@@ -47,6 +47,30 @@ extern "C" int impala_ingest(void* dev_slab, const void* host_slab, int64_t byte
     return e == cudaSuccess ? IMPALA_OK : (int)e;
 }
 
+// Columns [b0, b0 + B_local) of a host batch slab laid out for B columns -> a device slab laid out
+// for B_local columns: one strided 2-D copy per tensor (rows = time steps), the lens vector 1-D.
+extern "C" int impala_ingest_shard(void* dev_slab, const void* host_slab, int T, int B, int O, int A, int b0,
+                                   int B_local, void* stream) {
+    if (!dev_slab || !host_slab || b0 < 0 || B_local < 1 || b0 + B_local > B) return IMPALA_ERR_BAD_ARG;
+    int64_t ho[6], doff[6], ht, dt;
+    int rc = impala_batch_layout(T, B, O, A, ho, &ht);
+    if (rc != IMPALA_OK) return rc;
+    if ((rc = impala_batch_layout(T, B_local, O, A, doff, &dt)) != IMPALA_OK) return rc;
+    const int64_t width[5] = {(int64_t)O * 4, (int64_t)A * 4, 4, 4, 1};  // bytes per (step, column)
+    const int rows[5] = {T + 1, T, T, T, T};
+    const char* h = static_cast<const char*>(host_slab);
+    char* d = static_cast<char*>(dev_slab);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 5; ++i) {
+        cudaError_t e = cudaMemcpy2DAsync(d + doff[i], (size_t)B_local * width[i], h + ho[i] + (int64_t)b0 * width[i],
+                                          (size_t)B * width[i], (size_t)B_local * width[i], (size_t)rows[i],
+                                          cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaError_t e = cudaMemcpyAsync(d + doff[5], h + ho[5] + (int64_t)b0 * 4, (size_t)B_local * 4, cudaMemcpyHostToDevice, st);
+    return e == cudaSuccess ? IMPALA_OK : (int)e;
+}
+
 // ---- node-local peer buffers (CUDA IPC) for impala_allreduce_clip_adam
 extern "C" int impala_peer_alloc(int64_t bytes, void** dev_ptr, void* handle64) {
     if (bytes < 1 || !dev_ptr || !handle64) return IMPALA_ERR_BAD_ARG;

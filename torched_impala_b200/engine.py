@@ -282,6 +282,17 @@ class LearnerEngine:
                                            self.slab_bytes, C.c_void_p(cs.cuda_stream)), "impala_ingest")
         self.slab_ready[slot].record(cs)
 
+    def ingest_shard_from(self, host_address: int, b0: int, B_total: int, slot: int = 0) -> None:
+        """Data-parallel ingest: columns [b0, b0 + B_local) of a caller-owned (registered) host slab
+        laid out for B_total columns -> device slab `slot` (impala_ingest_shard)."""
+        cs = self.copy_stream
+        if self._slab_used[slot]:
+            cs.wait_event(self.slab_free[slot])
+        _cabi.check(self.lib.impala_ingest_shard(_ptr(self.d_slabs[slot]), C.c_void_p(host_address), self.T, B_total,
+                                                 self.O, self.A, b0, self.B, C.c_void_p(cs.cuda_stream)),
+                    "impala_ingest_shard")
+        self.slab_ready[slot].record(cs)
+
     def load_device_batch(self, batch: dict, slot: int = 0) -> None:
         """Convenience for kernel-only timing: put a batch in HBM and wait for it."""
         self.fill_host(batch, slot)
