@@ -145,9 +145,9 @@ def cpu_reference_numbers(warm: int, timed: int, budget_s: float = 120.0):
     learner.py:89: cost is linear in B) and labelled as such."""
     cores = os.cpu_count() or 1
     w = WORKLOAD
-    probe_B = min(32, w["B"])
+    probe_B = min(8, w["B"])  # tiny: with every host thread the per-trajectory python loop THRASHES (x100 slower)
     t1, kind = time_reference_learner(probe_B, 1, 1, 1)
-    tn, _ = time_reference_learner(probe_B, 1, 1, cores) if cores > 1 else (t1, kind)
+    tn, _ = time_reference_learner(probe_B, 0, 1, cores) if cores > 1 else (t1, kind)
     threads, per_traj = (1, t1 / probe_B) if t1 <= tn else (cores, tn / probe_B)
     sample_B = w["B"]
     while sample_B > 64 and per_traj * sample_B * (warm + timed) > budget_s:

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--payload", default="block", choices=["block", "trajectory"])
     ap.add_argument("--block", type=int, default=128)
     ap.add_argument("--publish-every", type=int, default=1)
+    ap.add_argument("--deadline", type=float, default=120.0)
     a = ap.parse_args()
     w = CFG[a.config]
     mp.set_start_method("fork", force=True)
@@ -84,16 +85,24 @@ def main():
     lrn.start()
     t_w = t_end = None
     v0 = None
-    deadline = time.time() + 600
+    deadline = time.time() + a.deadline
+    last_print = time.time()
     while time.time() < deadline and not lrn.completion.is_set():
         c = counter.value
+        if time.time() - last_print > 5:
+            last_print = time.time()
+            print(f"[e2e] {c} updates, filled={[int(x) for x in ring._control()['filled'].sum(1)]} "
+                  f"ticket={int(ring._control()['ticket'][0])} released={ring._control()['released'].tolist()} "
+                  f"version={lrn.policy_version}", file=sys.stderr, flush=True)
         if t_w is None and c >= a.warmup:
             t_w, c_w, v0 = time.perf_counter(), c, lrn.policy_version
         if c >= a.updates:
             break
         time.sleep(0.0005)
     t_end, c_end = time.perf_counter(), counter.value
-    ok = lrn.completion.wait(timeout=120)
+    ok = lrn.completion.wait(timeout=30)
+    if not ok:
+        lrn.terminate()
     lrn.join()
     for p in actors:
         p.join(timeout=5)

@@ -16,8 +16,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "lib", "obj")
-LIB = os.path.join(HERE, "lib", "libimpala_b200.so")
+# IMPALA_LIB_DIR: build somewhere else (compile checks while a snapshot of the tree is in flight)
+_LIB_DIR = os.environ.get("IMPALA_LIB_DIR", os.path.join(HERE, "lib"))
+OBJ = os.path.join(_LIB_DIR, "obj")
+LIB = os.path.join(_LIB_DIR, "libimpala_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -79,6 +79,32 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
     return x;
 }
 
+// ---- programmatic dependent launch (PDL): the kernels of a learner step are launched so that
+// kernel k + 1 may be scheduled while kernel k is still running: each kernel calls
+// pdl_launch_dependents() first thing (its successor may start occupying free SM resources and
+// run its own prologue - barrier init, TMEM allocation, weight staging, optimizer-state loads)
+// and pdl_wait() before the first access to anything its predecessor produces (returns at once
+// when the launch had no programmatic predecessor).  Inside a captured CUDA graph these become
+// programmatic edges.  IMPALA_PDL=0 restores plain stream-ordered launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, bool dependent, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    unsigned n = 0;
+    if (dependent && impala_env_int("IMPALA_PDL", 1) != 0) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        n = 1;
+    }
+    cfg.attrs = attr, cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- push-model all-reduce over peer memory (protocol: see optim.cu)
 struct PushArgs {
     double* const* gather;     // device array [world]: every rank's gather buffer (peer-mapped)

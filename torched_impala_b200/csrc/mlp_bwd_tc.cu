@@ -111,6 +111,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     Barriers* bars = reinterpret_cast<Barriers*>(exch + (NP + 1) * 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();  // the optimizer kernel may be scheduled (and load its state) meanwhile
     const float* __restrict__ W1 = a.params + a.lay.oW1;
     const float* __restrict__ b1 = a.params + a.lay.ob1;
     const float* __restrict__ W2 = a.params + a.lay.oW2;
@@ -154,10 +155,16 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             tc::bulk_g2s(dst + kRawDzOffset, a.dout + row0 * a.N2, bytes_z, &bars->raw_full[rs]);
         }
     };
-    if (warp == 16 && lane == 0)
+    // Everything up to here - and the W1' staging / TMEM allocation below - only touches parameters
+    // and this kernel's own state; dout (dlogits / dv) is the V-trace kernel's output: the thread
+    // that issues the bulk copies waits for it now, everybody else after staging (PDL, common.cuh).
+    if (warp == 16 && lane == 0) {
+        pdl_wait();
         for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
+    }
     if (warp == 18) tc::tmem_alloc(&bars->tmem_base, 512);
     tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/false);
+    pdl_wait();
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -637,7 +644,7 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     }
     int grid = a.num_tiles < sms ? a.num_tiles : sms;  // <= SM count: the grid barrier needs residency
     if (grid > kMaxParts) grid = kMaxParts;
-    kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+    if ((e = impala_launch(kernel, grid, kThreads, kSmemBytes, st, true, a)) != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
@@ -669,8 +676,10 @@ int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* 
     const int n_pi = impala_pair_split(a_pi.num_tiles, a_vf.num_tiles, grid,
                                        impala_env_int("IMPALA_PAIR_W_BWD", 127) * (H_pi / 128),
                                        100 * (H_vf / 128));
-    if (push) mlp_bwd_tc_pair_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi, *push, extra, n_extra);
-    else mlp_bwd_tc_pair_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(a_pi, a_vf, n_pi, PushArgs{}, nullptr, 0);
+    e = push ? impala_launch(mlp_bwd_tc_pair_kernel<true>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, *push, extra, n_extra)
+             : impala_launch(mlp_bwd_tc_pair_kernel<false>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, PushArgs{},
+                             (const double*)nullptr, 0);
+    if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 

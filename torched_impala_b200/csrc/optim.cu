@@ -45,12 +45,17 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
     float pk[kKeep], mk[kKeep], vk[kKeep];
     double ss0 = 0.0, ss1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < kKeep; ++k) {
+    for (int k = 0; k < kKeep; ++k) {  // optimizer state: not touched by the backward, loaded before the wait
         const int64_t i = first + k * stride;
-        gk[k] = i < n_total ? grad[i] : 0.0;
         pk[k] = i < n_total ? params[i] : 0.f;
         mk[k] = i < n_total ? m[i] : 0.f;
         vk[k] = i < n_total ? v[i] : 0.f;
+    }
+    pdl_wait();  // the gradient comes from the backward kernel
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+        const int64_t i = first + k * stride;
+        gk[k] = i < n_total ? grad[i] : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < kKeep; ++k) {
@@ -157,6 +162,8 @@ constexpr int kPushCtas = 16, kPushThreads = 256;
 // ctl: one zeroed word (CTA count-out), re-armed by the last CTA.
 __global__ void __launch_bounds__(kPushThreads)
 peer_push_kernel(const double* __restrict__ local, int64_t n, PushArgs p, unsigned int* ctl) {
+    pdl_launch_dependents();
+    pdl_wait();  // `local` comes from the backward kernel
     const long long step = *p.seq + 1;
     const int64_t off = (step & 1) * p.buf_stride + (int64_t)p.rank * p.slot_stride;
     const int64_t n2 = n >> 1;  // double2 granularity (n is padded to an even count by the caller)
@@ -208,6 +215,7 @@ gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced
         mk[k] = i < n_total ? m[i] : 0.f;
         vk[k] = i < n_total ? v[i] : 0.f;
     }
+    pdl_wait();  // flags / slots of this rank's own contribution come from the backward (or push) kernel
     if (warp == 0) {
         const long long step = *seq + 1;
         int gave_up = 0;
@@ -332,8 +340,9 @@ extern "C" int impala_clip_adam(float* params, const double* grad, float* m, flo
                                 void* stream) {
     if (!params || !grad || !m || !v || !state) return IMPALA_ERR_BAD_ARG;
     if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
-    clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
-        params, grad, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
+    const cudaError_t e = impala_launch(clip_adam_kernel, kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream, true, params,
+                                        grad, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out);
+    if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
@@ -345,7 +354,8 @@ extern "C" int impala_peer_push(const double* local, int64_t n, double* const* p
     if (slot_stride < n || (slot_stride & 1) || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(local) & 15) != 0) return IMPALA_ERR_BAD_ARG;
     PushArgs p{peer_gather, peer_flags, seq, slot_stride, buf_stride, rank, world};
-    peer_push_kernel<<<kPushCtas, kPushThreads, 0, (cudaStream_t)stream>>>(local, n, p, ctl);
+    const cudaError_t e = impala_launch(peer_push_kernel, kPushCtas, kPushThreads, 0, (cudaStream_t)stream, true, local, n, p, ctl);
+    if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
@@ -361,8 +371,9 @@ extern "C" int impala_gather_clip_adam(float* params, double* reduced, const dou
     if (slot_stride < n_total + n_extra || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
     const unsigned long long timeout_ns =
         timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 600ull * 1000000000ull;
-    gather_clip_adam_kernel<<<kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream>>>(
-        params, reduced, gather, flags, seq, slot_stride, buf_stride, world, n_extra, m, v, state, n_policy,
-        n_total, max_norm, lr, beta1, beta2, eps, norms_out, err, timeout_ns);
+    const cudaError_t e = impala_launch(gather_clip_adam_kernel, kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream, true,
+                                        params, reduced, gather, flags, seq, slot_stride, buf_stride, world, n_extra, m, v,
+                                        state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out, err, timeout_ns);
+    if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }

@@ -126,6 +126,8 @@ template <int AP, int S, int MAXT, int MINB, bool WITH_LOSS, bool VEC>
 __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a) {
     __shared__ float2 s_map[2][kMaxSeg][32];
     __shared__ double s_red[kMaxSeg][4];
+    pdl_launch_dependents();
+    pdl_wait();  // logits / values come from the forward kernel
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nseg = blockDim.x >> 5;
     const int T = a.T, B = a.B, A = VEC ? AP : a.A;
     const int b = blockIdx.x * 32 + lane;
@@ -139,62 +141,67 @@ __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a)
 
     double sum_vl = 0.0, sum_pl = 0.0, sum_ent = 0.0, sum_rw = 0.0;
     float chunk_carry = 0.f;  // accumulator at the first step after the current chunk
-    for (int c = nch - 1; c >= 0; --c) {
-        const int tb = c * rows + w * S;  // first step of this thread's segment
-        // ---- 1. loads.  Unpredicated: steps past the unroll (last chunk only) re-read step T - 1 and
-        // dead lanes read trajectory B - 1; both are masked by `valid` below (rho = c = disc = 0).
+    // One chunk's raw rows of this thread (registers).  Unpredicated loads: steps past the unroll
+    // (last chunk only) re-read step T - 1 and dead lanes read trajectory B - 1; both are masked
+    // by `valid` below (rho = c = disc = 0).
+    struct Rows {
         float zc[S][AP], zb[S][AP], r[S], vv[S + 1];
         int act[S];
-        bool dn[S];
+        unsigned char dn[S];  // raw: compared where it is used, so the load is not waited for at issue
+    };
+    auto load_rows = [&](Rows& R, const int c) {
+        const int tb = c * rows + w * S;
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const unsigned e = (unsigned)min(tb + i, T - 1) * (unsigned)B + (unsigned)bl;
-            load_logits<AP, VEC>(a.cur_logits, e, A, zc[i]);
-            load_logits<AP, VEC>(a.beh_logits, e, A, zb[i]);
-            r[i] = __ldg(a.rewards + e);
-            act[i] = __ldg(a.actions + e);
-            dn[i] = __ldg(a.done + e) != 0;
+            load_logits<AP, VEC>(a.cur_logits, e, A, R.zc[i]);
+            load_logits<AP, VEC>(a.beh_logits, e, A, R.zb[i]);
+            R.r[i] = __ldg(a.rewards + e);
+            R.act[i] = __ldg(a.actions + e);
+            R.dn[i] = __ldg(a.done + e);
         }
 #pragma unroll
-        for (int i = 0; i <= S; ++i) vv[i] = __ldg(a.v + (unsigned)min(tb + i, T) * (unsigned)B + (unsigned)bl);
-
+        for (int i = 0; i <= S; ++i) R.vv[i] = __ldg(a.v + (unsigned)min(tb + i, T) * (unsigned)B + (unsigned)bl);
+    };
+    auto process = [&](Rows& R, const int c) {
+        const int tb = c * rows + w * S;  // first step of this thread's segment
         // ---- 2. per-step terms and the zero-carry scan of this segment
         float rho[S], disc[S], fa[S], g[S], lp2a[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const bool valid = tb + i < L;
             // log-softmax of both logit vectors in the base-2 domain (learner.py:298-303)
-            float mx = zc[i][0], mxb = zb[i][0];
+            float mx = R.zc[i][0], mxb = R.zb[i][0];
 #pragma unroll
             for (int k = 1; k < AP; ++k)
-                if (k < A) mx = fmaxf(mx, zc[i][k]), mxb = fmaxf(mxb, zb[i][k]);
+                if (k < A) mx = fmaxf(mx, R.zc[i][k]), mxb = fmaxf(mxb, R.zb[i][k]);
             float se = 0.f, seb = 0.f;
 #pragma unroll
             for (int k = 0; k < AP; ++k) {
-                zc[i][k] = (zc[i][k] - mx) * kLog2e;
-                zb[i][k] = (zb[i][k] - mxb) * kLog2e;
-                if (k < A) se += ex2f(zc[i][k]), seb += ex2f(zb[i][k]);
+                R.zc[i][k] = (R.zc[i][k] - mx) * kLog2e;
+                R.zb[i][k] = (R.zb[i][k] - mxb) * kLog2e;
+                if (k < A) se += ex2f(R.zc[i][k]), seb += ex2f(R.zb[i][k]);
             }
             const float lse = lg2f(se), lseb = lg2f(seb);
-            float z_a = zc[i][0], zb_a = zb[i][0];
+            float z_a = R.zc[i][0], zb_a = R.zb[i][0];
 #pragma unroll
             for (int k = 1; k < AP; ++k) {
-                const bool hit = k == act[i];
-                z_a = selp_f32(hit, zc[i][k], z_a), zb_a = selp_f32(hit, zb[i][k], zb_a);
+                const bool hit = k == R.act[i];
+                z_a = selp_f32(hit, R.zc[i][k], z_a), zb_a = selp_f32(hit, R.zb[i][k], zb_a);
             }
 #pragma unroll
-            for (int k = 0; k < AP; ++k) zc[i][k] -= lse;  // log2 pi(k)
+            for (int k = 0; k < AP; ++k) R.zc[i][k] -= lse;  // log2 pi(k)
             lp2a[i] = z_a - lse;                                               // log2 pi(a)
             const float ratio = ex2f(lp2a[i] - (zb_a - lseb));                 // :121-123
             rho[i] = valid ? fminf(ratio, a.rho_bar) : 0.f;                    // :124
             const float cc = valid ? fminf(ratio, a.c_bar) : 0.f;              // :125
-            disc[i] = (valid && !dn[i]) ? a.gamma : 0.f;                       // :109
+            disc[i] = (valid && R.dn[i] == 0) ? a.gamma : 0.f;                       // :109
             g[i] = disc[i] * cc;
             if (ref_mode) {
-                const float delta = rho[i] * (r[i] + a.gamma * vv[i + 1] - v0);  // :126
-                fa[i] = delta - g[i] * vv[i + 1];                                // :130
+                const float delta = rho[i] * (R.r[i] + a.gamma * R.vv[i + 1] - v0);  // :126
+                fa[i] = delta - g[i] * R.vv[i + 1];                                // :130
             } else {
-                fa[i] = rho[i] * (r[i] + disc[i] * vv[i + 1] - vv[i]);
+                fa[i] = rho[i] * (R.r[i] + disc[i] * R.vv[i + 1] - R.vv[i]);
             }
         }
         float acc[S + 1], P[S];
@@ -225,26 +232,26 @@ __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a)
             const int t = tb + i;
             const bool valid = t < L;
             acc[i] = fmaf(P[i], mine, acc[i]);
-            const float vs_n = acc[i + 1] + vv[i + 1];                         // :131
-            const float pg = rho[i] * (r[i] + disc[i] * vs_n - vv[i]);         // :135
+            const float vs_n = acc[i + 1] + R.vv[i + 1];                         // :131
+            const float pg = rho[i] * (R.r[i] + disc[i] * vs_n - R.vv[i]);         // :135
             const unsigned e = (unsigned)t * (unsigned)B + (unsigned)b;
             if (live && t < T) {
-                if (a.vs) a.vs[e] = (t <= L) ? acc[i] + vv[i] : 0.f;
+                if (a.vs) a.vs[e] = (t <= L) ? acc[i] + R.vv[i] : 0.f;
                 if (a.pg_adv) a.pg_adv[e] = pg;  // rho == 0 on padding
-                if (t == T - 1 && a.vs) a.vs[e + B] = (L == T) ? vv[i + 1] : 0.f;  // bootstrap row
+                if (t == T - 1 && a.vs) a.vs[e + B] = (L == T) ? R.vv[i + 1] : 0.f;  // bootstrap row
             }
             if constexpr (WITH_LOSS) {
                 // d total / d v = v_loss_c (v - vs) / B = -v_loss_c acc / B  (:149, :306-307)
                 float ent = 0.f, pk[AP], lz[AP], dz[AP];
 #pragma unroll
                 for (int k = 0; k < AP; ++k) {
-                    lz[k] = zc[i][k] * kLn2;
-                    pk[k] = (k < A) ? ex2f(zc[i][k]) : 0.f;
+                    lz[k] = R.zc[i][k] * kLn2;
+                    pk[k] = (k < A) ? ex2f(R.zc[i][k]) : 0.f;
                     if (k < A) ent -= pk[k] * lz[k];                           // :310-314, :153
                 }
 #pragma unroll
                 for (int k = 0; k < AP; ++k) {
-                    const float onehot = (k == act[i]) ? 1.f : 0.f;
+                    const float onehot = (k == R.act[i]) ? 1.f : 0.f;
                     const float d = a.inv_batch * (a.policy_loss_c * pg * (pk[k] - onehot) +
                                                    a.entropy_c * pk[k] * (lz[k] + ent));
                     dz[k] = (valid && k < A) ? d : 0.f;
@@ -258,9 +265,26 @@ __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a)
                     sum_vl += 0.5 * (double)acc[i] * (double)acc[i];
                     sum_pl += (double)(-(lp2a[i] * kLn2) * pg);                // :317-321
                     sum_ent += (double)ent;
-                    sum_rw += (double)r[i];                                    // :108
+                    sum_rw += (double)R.r[i];                                    // :108
                 }
             }
+        }
+    };
+    // Chunks are walked backwards with the NEXT chunk's loads already in flight while the current one
+    // is processed (two register sets, loop unrolled by two): without it every CTA alternates between
+    // a pure memory phase and a pure compute phase and, all CTAs having started together, so does
+    // the whole GPU.
+    {
+        Rows R0, R1;
+        int c = nch - 1;
+        load_rows(R0, c);
+        while (true) {
+            if (c > 0) load_rows(R1, c - 1);
+            process(R0, c);
+            if (--c < 0) break;
+            if (c > 0) load_rows(R0, c - 1);
+            process(R1, c);
+            if (--c < 0) break;
         }
     }
 
@@ -320,8 +344,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 template <int AP, int S, int MAXT, int MINB, bool WITH_LOSS>
 int launch_s(const VtArgs& a, bool vec, unsigned grid, int nseg, cudaStream_t st) {
-    if (vec) vtrace_lane_kernel<AP, S, MAXT, MINB, WITH_LOSS, true><<<grid, 32 * nseg, 0, st>>>(a);
-    else vtrace_lane_kernel<AP, S, MAXT, MINB, WITH_LOSS, false><<<grid, 32 * nseg, 0, st>>>(a);
+    const cudaError_t e = vec ? impala_launch(vtrace_lane_kernel<AP, S, MAXT, MINB, WITH_LOSS, true>, grid, 32 * nseg, 0, st, true, a)
+                              : impala_launch(vtrace_lane_kernel<AP, S, MAXT, MINB, WITH_LOSS, false>, grid, 32 * nseg, 0, st, true, a);
+    if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
@@ -347,10 +372,10 @@ int launch(VtArgs& a, cudaStream_t st) {
     if (nseg > max_seg) nseg = max_seg;
     const int n_env = impala_env_int("IMPALA_VTRACE_NSEG", 0);
     if (n_env >= 1 && n_env <= max_seg) nseg = n_env;
-    if (AP == 2) return S == 5 ? launch_s<2, 5, 320, 2, WITH_LOSS>(a, vec, grid, nseg, st)
-                               : launch_s<2, 2, 512, 2, WITH_LOSS>(a, vec, grid, nseg, st);
-    if (AP == 4) return S == 5 ? launch_s<4, 5, 320, 2, WITH_LOSS>(a, vec, grid, nseg, st)
-                               : launch_s<4, 2, 512, 2, WITH_LOSS>(a, vec, grid, nseg, st);
+    if (AP == 2) return S == 5 ? launch_s<2, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st)
+                               : launch_s<2, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
+    if (AP == 4) return S == 5 ? launch_s<4, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st)
+                               : launch_s<4, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
     if (AP == 8) return launch_s<8, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
     return launch_s<16, 1, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
 }

@@ -362,16 +362,18 @@ class LearnerEngine:
         return 1
 
     def _capture(self, slot: int):
+        # thread_local: other host threads of the learner process (weight publisher, evaluation) keep
+        # making CUDA calls while this thread captures
         with torch.cuda.stream(self.stream):
             g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, stream=self.stream):
+            with torch.cuda.graph(g1, stream=self.stream, capture_error_mode="thread_local"):
                 self._main_launches = self._enqueue_main(slot)
                 if self._one_graph():  # no library collective in between: the optimizer joins the graph
                     self._enqueue_opt()
             self._graph_main[slot] = g1
             if not self._one_graph() and self._graph_opt is None:
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, stream=self.stream):
+                with torch.cuda.graph(g2, stream=self.stream, capture_error_mode="thread_local"):
                     self._enqueue_opt()
                 self._graph_opt = g2
 
