@@ -288,8 +288,7 @@ def kernel_breakdown(eng, flush, iters=20, barrier=lambda: None):
         "mlp_backward_pair(policy+value_fn)": (lambda: lib.impala_mlp_backward_pair_push(
             obs, p_pi, p_vf, _ptr(eng.dlogits), _ptr(eng.dv), _ptr(eng.ws_pi), eng.ws_pi_bytes, _ptr(eng.ws_vf),
             eng.ws_vf_bytes, eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, scal, 4, _ptr(eng.peer["gather_ptrs"]),
-            _ptr(eng.peer["flag_ptrs"]), _ptr(eng.peer["seq"]), eng.peer["slot"], eng.peer["buf"], eng.peer["rank"],
-            eng.world, st)) if (eng.peer and eng.peer["fused"]) else (lambda: lib.impala_mlp_backward_pair(
+            _ptr(eng.peer["seq"]), eng.peer["slot"], eng.peer["buf"], eng.peer["rank"], eng.world, st)) if (eng.peer and eng.peer["fused"]) else (lambda: lib.impala_mlp_backward_pair(
             obs, p_pi, p_vf, _ptr(eng.dlogits), _ptr(eng.dv), g_pi, g_vf, _ptr(eng.ws_pi), eng.ws_pi_bytes,
             _ptr(eng.ws_vf), eng.ws_vf_bytes, eng.M_pi, eng.M_vf, O, eng.H_pi, eng.H_v, A, st)),
         # the per-network entry points, for comparison (not launched by the step)
@@ -373,9 +372,8 @@ def kernel_breakdown(eng, flush, iters=20, barrier=lambda: None):
             if pr:  # this step's contribution -> every rank (stand-alone producer), timed on its own
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(eng.stream)
-                _cabi.check(lib.impala_peer_push(_ptr(eng.comm), eng.n_total + 8, _ptr(pr["gather_ptrs"]),
-                                                 _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"],
-                                                 eng.world, _ptr(pr["ctl"]), st), "impala_peer_push")
+                _cabi.check(lib.impala_peer_push(_ptr(eng.comm), eng.n_total + 8, _ptr(pr["gather_ptrs"]), _ptr(pr["seq"]),
+                                                 pr["slot"], pr["buf"], pr["rank"], eng.world, st), "impala_peer_push")
                 e1.record(eng.stream)
                 ts_push.append((e0, e1))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -386,12 +384,12 @@ def kernel_breakdown(eng, flush, iters=20, barrier=lambda: None):
             ts.append(e0.elapsed_time(e1) * 1e3)
         for dst, src in zip((eng.params, eng.adam_m, eng.adam_v, eng.adam_step), keep):
             dst.copy_(src)
-        # read grad f64 (world local slots when the gradient was pushed over peer memory) + params/m/v rw
+        # read grad (N = 1: f64; N > 1: `world` local 16-byte LL elements per entry) + params/m/v rw
         out["gather+clip_adam" if pr else "clip_adam"] = dict(
-            us=statistics.median(ts), flops=None, bytes=(8.0 * eng.world + 6 * 4.0) * eng.n_total)
+            us=statistics.median(ts), flops=None, bytes=((16.0 * eng.world if pr else 8.0) + 6 * 4.0) * eng.n_total)
         if pr:
             out["peer_push(stand-alone)"] = dict(us=statistics.median([a.elapsed_time(b) * 1e3 for a, b in ts_push]),
-                                                 flops=None, bytes=8.0 * eng.world * (eng.n_total + 8))
+                                                 flops=None, bytes=16.0 * eng.world * (eng.n_total + 8))
     eng.synchronize()
     return out
 
@@ -631,7 +629,7 @@ def run_own_arm(args):
         warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True, scaling="strong",
         vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=WORKLOAD_NAME, **w, global_batch=w["B"], per_gpu_batch=Bl,
-                    parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step, "
+                    parallelism=f"dp{world} (batch sharded, 1 all-reduce of {8 * (eng.n_total + 8)} B/step (16-byte LL elements on the wire), "
                                 f"{('pushed over NVLink peer memory from the ' + ('backward kernel tail' if eng.peer['fused'] else 'stand-alone producer kernel')) if eng.peer else 'NCCL'})"
                     if world > 1 else "single GPU",
                     l2="flushed between timed steps (256 MiB memset on the launching stream)",

@@ -166,52 +166,49 @@ int impala_peer_close(void* dev_ptr);
 int impala_peer_free(void* dev_ptr);
 
 /* Data-parallel learners on one NVLink node (one process per GPU): the gradient all-reduce
- * without a collective library call, as a PUSH over peer-mapped memory.  Replaces the
+ * without a collective library call, as a PUSH over peer-mapped memory in LL format.  Replaces the
  * DistributedDataParallel-style all-reduce a multi-GPU port of learner.py:175-183 would place
  * between loss.backward() and optimizer.step().
  *
- * Every rank owns a float64 gather buffer  G[2 parities][world slots][slot_stride]  (parities
- * buf_stride doubles apart, zero-filled once) and a flag block int64[world] (zero-filled once),
- * both mapped by all ranks; peer_gather[r] / peer_flags[r] are THIS process's device pointers to
- * rank r's buffer / flag block (own entries included), both arrays in device memory.  `seq` is
- * a device int64 (zero-filled once) counting completed optimizer calls; step s = *seq + 1 uses
- * parity s & 1.
+ * Every rank owns a gather buffer  G[2 parities][world slots][slot_stride]  of 16-byte LL elements
+ * (parities buf_stride elements apart, zero-filled once) mapped by all ranks; peer_gather[r] is
+ * THIS process's device pointer to rank r's buffer (own entry included), the array itself in
+ * device memory.  An LL element carries one float64 as [lo32 | step32 | hi32 | step32]: each
+ * 8-byte half is tagged with the step it belongs to, so data and "ready" travel in the same
+ * posted NVLink write - no fence, no flag, no acknowledgement.  `seq` is a device int64
+ * (zero-filled once) counting completed optimizer calls; step s = *seq + 1 uses parity s & 1.
  *   producer  stores this rank's [gradient (n_total) | n_extra logged scalars] of step s into slot
- *             `rank` of EVERY rank's buffer (posted NVLink writes), then releases flag[rank] = s on
- *             every rank:  impala_mlp_backward_pair_push does it in the tail of the paired
- *             tensor-core backward kernel (no extra launch); impala_peer_push is the stand-alone
- *             producer for shapes that kernel does not cover (after impala_mlp_backward[_pair]).
- *   consumer  impala_gather_clip_adam waits until the LOCAL flag block shows step s for all ranks,
- *             adds the `world` local slots of each entry in rank order (bit-identical sums on every
- *             rank), writes them to `reduced` ([n_total + n_extra], local), applies
- *             impala_clip_adam's update and advances *seq.
- * The parity buffers replace a second handshake (a slot is rewritten two steps later, after the
- * flags of the step in between proved that every peer has finished reading it).  Every rank
- * must make the same sequence of calls.  A rank that never arrives does not kill the others:
+ *             `rank` of EVERY rank's buffer: impala_mlp_backward_pair_push does it in the tail of
+ *             the paired tensor-core backward kernel (no extra launch); impala_peer_push is the
+ *             stand-alone producer for shapes that kernel does not cover (after
+ *             impala_mlp_backward[_pair]).
+ *   consumer  impala_gather_clip_adam polls the `world` LOCAL slots of each entry until they carry
+ *             step s, adds them in rank order (bit-identical sums on every rank), writes them to
+ *             `reduced` ([n_total + n_extra], local), applies impala_clip_adam's update and
+ *             advances *seq.
+ * The parity buffers replace a "slot consumed" message (a slot is rewritten two steps later, after
+ * the values of the step in between proved that every peer has finished reading it).  Every rank
+ * must make the same sequence of calls.  A rank that never delivers does not kill the others:
  * after timeout_s (<= 0: 600 s) the consumer sets *err = 1 (device int, may be NULL), leaves
  * parameters / optimizer state / seq untouched and returns normally. */
-/* local: 16-byte aligned, n even (pad with zeros); ctl: one device word, zero-filled once. */
-int impala_peer_push(const double* local, int64_t n, double* const* peer_gather,
-                     long long* const* peer_flags, const long long* seq, int64_t slot_stride,
-                     int64_t buf_stride, int rank, int world, unsigned int* ctl, void* stream);
+int impala_peer_push(const double* local, int64_t n, void* const* peer_gather, const long long* seq,
+                     int64_t slot_stride, int64_t buf_stride, int rank, int world, void* stream);
 /* 1 when impala_mlp_backward_pair_push covers these shapes (tensor-core paired backward). */
 int impala_mlp_backward_pair_push_supported(int M_pi, int M_vf, int O, int H_pi, int H_vf, int A);
 /* impala_mlp_backward_pair whose reduction tail pushes [grad_pi | grad_vf | extra[0..n_extra)] to
- * the peers and posts the flags; `extra` = this rank's local scalars (device, read by the kernel). */
+ * the peers; `extra` = this rank's local scalars (device, read by the kernel). */
 int impala_mlp_backward_pair_push(const float* x, const float* params_pi, const float* params_vf,
                                   const float* dlogits, const float* dv, void* workspace_pi,
                                   int64_t workspace_pi_bytes, void* workspace_vf,
                                   int64_t workspace_vf_bytes, int M_pi, int M_vf, int O, int H_pi,
                                   int H_vf, int A, const double* extra, int n_extra,
-                                  double* const* peer_gather, long long* const* peer_flags,
-                                  const long long* seq, int64_t slot_stride, int64_t buf_stride,
-                                  int rank, int world, void* stream);
-int impala_gather_clip_adam(float* params, double* reduced, const double* gather,
-                            const long long* flags, long long* seq, int64_t slot_stride,
-                            int64_t buf_stride, int world, int n_extra, float* m, float* v,
-                            int64_t* state, int64_t n_policy, int64_t n_total, float max_norm,
-                            float lr, float beta1, float beta2, float eps, double* norms_out,
-                            int* err, double timeout_s, void* stream);
+                                  void* const* peer_gather, const long long* seq, int64_t slot_stride,
+                                  int64_t buf_stride, int rank, int world, void* stream);
+int impala_gather_clip_adam(float* params, double* reduced, const void* gather, long long* seq,
+                            int64_t slot_stride, int64_t buf_stride, int world, int n_extra, float* m,
+                            float* v, int64_t* state, int64_t n_policy, int64_t n_total,
+                            float max_norm, float lr, float beta1, float beta2, float eps,
+                            double* norms_out, int* err, double timeout_s, void* stream);
 
 /* Pieces of the reference's module-level loss helpers (learner.py:298-321) for callers that use
  * them individually instead of impala_vtrace_loss.  logits (M,A) f32 row-major, actions (M) i32.

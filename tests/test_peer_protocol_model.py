@@ -1,23 +1,26 @@
-"""CPU model of the push all-reduce handshake (csrc/optim.cu, tail of csrc/mlp_bwd_tc.cu).
+"""CPU model of the push all-reduce handshake (csrc/optim.cu, tail of csrc/mlp_bwd_tc.cu), LL format.
 
-Protocol: the backward of step s on rank `me` STORES its contribution into slot `me` of parity
-s & 1 in EVERY rank's gather buffer, then posts flag[me] = s on every rank; the optimizer of step s
-waits until its own flag block shows s for all ranks, then reads its own `world` slots.  The
-safety argument - parity-double-buffered slots need only the "ready" flags, no acknowledgement
-round trip - is a protocol property, independent of CUDA: rank threads with random delays run it
-here and check that every read returns exactly the step it expects (never a slot a fast peer has
-already overwritten, never a stale one).  The same model with ONE buffer per rank must fail,
-which shows the test can see the hazard the second buffer removes."""
+Protocol: the backward of step s on rank `me` STORES each value of its contribution, tagged with s,
+into slot `me` of parity s & 1 in EVERY rank's gather buffer (no flag, no fence); the optimizer of
+step s polls its own `world` slots until every element carries tag s, then uses them.  The safety
+argument - parity-double-buffered slots need no acknowledgement round trip - is a protocol
+property, independent of CUDA: rank threads with random delays run it here, writing element by
+element with pauses (so readers do see half-written slots), and check that every value a reader
+accepts is exactly the one the writer sent for that step (never a value a fast peer has already
+overwritten).  The same model with ONE buffer per rank must fail, which shows the test can see the
+hazard the second buffer removes."""
 import random
 import threading
 import time
 
 import pytest
 
+ELEMS = 6
+
 
 def run_ranks(world: int, steps: int, buffers: int, seed: int):
-    gather = [[[0] * world for _ in range(buffers)] for _ in range(world)]  # gather[owner][parity][writer] = step
-    flags = [[0] * world for _ in range(world)]          # flags[owner][writer] = last step `writer` posted
+    # gather[owner][parity][writer][element] = (tag, payload)
+    gather = [[[[(0, None)] * ELEMS for _ in range(world)] for _ in range(buffers)] for _ in range(world)]
     errors, stop = [], threading.Event()
 
     def rank(me: int):
@@ -26,19 +29,30 @@ def run_ranks(world: int, steps: int, buffers: int, seed: int):
             if stop.is_set():
                 return
             time.sleep(rng.random() * 2e-4)              # forward / V-trace / backward of step s ...
-            for p in range(world):                       # ... whose tail pushes the gradient to everyone
-                gather[p][s % buffers][me] = s
-            for p in range(world):                       # last CTA out: release the flags
-                flags[p][me] = s
+            for e in range(ELEMS):                       # ... whose tail pushes tagged values to everyone
+                for p in range(world):
+                    gather[p][s % buffers][me][e] = (s, (me, s, e))
+                if rng.random() < 0.2:
+                    time.sleep(0)                        # a reader may observe a half-written slot
             t0 = time.time()
-            while any(flags[me][r] < s for r in range(world)):   # optimizer: wait on the LOCAL flag block
-                if stop.is_set() or time.time() - t0 > 20:
-                    return
-                time.sleep(0)
-            if rng.random() < 0.3:
-                time.sleep(rng.random() * 3e-4)          # a slow reader
-            got = list(gather[me][s % buffers])          # local slots, rank order
-            if got != [s] * world:
+            got = []
+            for r in range(world):                       # optimizer: poll the LOCAL slots element by element
+                for e in range(ELEMS):
+                    while True:
+                        tag, val = gather[me][s % buffers][r][e]
+                        if tag == s:
+                            break
+                        if stop.is_set() or time.time() - t0 > 20:
+                            return
+                        if tag > s:                      # overwritten before it was read: the hazard
+                            errors.append((me, s, r, e, tag))
+                            stop.set()
+                            return
+                        time.sleep(0)
+                    got.append(val)
+                if rng.random() < 0.1:
+                    time.sleep(rng.random() * 3e-4)      # a slow reader
+            if got != [(r, s, e) for r in range(world) for e in range(ELEMS)]:
                 errors.append((me, s, got))
                 stop.set()
                 return
@@ -47,17 +61,17 @@ def run_ranks(world: int, steps: int, buffers: int, seed: int):
     for t in ts:
         t.start()
     for t in ts:
-        t.join(timeout=60)
+        t.join(timeout=90)
     return errors
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_parity_buffers_need_no_acknowledgement(world):
     for seed in range(3):
-        assert run_ranks(world, steps=300, buffers=2, seed=seed) == []
+        assert run_ranks(world, steps=150, buffers=2, seed=seed) == []
 
 
 def test_single_buffer_is_unsafe_without_acknowledgement():
     """Sanity of the model itself: with one buffer a fast rank overwrites what a slow rank has not
     read yet - the hazard must show up within a few attempts."""
-    assert any(run_ranks(4, steps=300, buffers=1, seed=seed) for seed in range(8))
+    assert any(run_ranks(4, steps=150, buffers=1, seed=seed) for seed in range(8))

@@ -41,10 +41,10 @@ SIGNATURES = {
     "impala_peer_open": (_i, [_p, _p]),
     "impala_peer_close": (_i, [_p]),
     "impala_peer_free": (_i, [_p]),
-    "impala_peer_push": (_i, [_p, _i64, _p, _p, _p, _i64, _i64, _i, _i, _p, _p]),
+    "impala_peer_push": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _p]),
     "impala_mlp_backward_pair_push_supported": (_i, [_i] * 6),
-    "impala_mlp_backward_pair_push": (_i, [_p] * 6 + [_i64, _p, _i64] + [_i] * 6 + [_p, _i, _p, _p, _p, _i64, _i64, _i, _i, _p]),
-    "impala_gather_clip_adam": (_i, [_p] * 5 + [_i64, _i64, _i, _i, _p, _p, _p, _i64, _i64] + [_f] * 5
+    "impala_mlp_backward_pair_push": (_i, [_p] * 6 + [_i64, _p, _i64] + [_i] * 6 + [_p, _i, _p, _p, _i64, _i64, _i, _i, _p]),
+    "impala_gather_clip_adam": (_i, [_p] * 4 + [_i64, _i64, _i, _i, _p, _p, _p, _i64, _i64] + [_f] * 5
                                 + [_p, _p, C.c_double, _p]),
     "impala_vtrace": (_i, [_p] * 9 + [_i, _i, _i, _f, _f, _f, _i, _p]),
     "impala_vtrace_loss_workspace": (_i64, [_i, _i, _i]),

@@ -105,20 +105,32 @@ static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// ---- push-model all-reduce over peer memory (protocol: see optim.cu)
+// ---- push-model all-reduce over peer memory, LL ("low latency") format (protocol: see optim.cu)
+// One float64 travels as 16 bytes  [lo32 | step32 | hi32 | step32] : each 8-byte half carries the
+// step number it belongs to, 8-byte stores are single NVLink transactions, so a reader that sees
+// both halves tagged with the step it is waiting for has the value - no fence, no separate flag,
+// no acknowledgement on the data path.
 struct PushArgs {
-    double* const* gather;     // device array [world]: every rank's gather buffer (peer-mapped)
-    long long* const* flags;   // device array [world]: every rank's flag block
-    const long long* seq;      // this rank's step counter (device, 1 word)
-    int64_t slot_stride;       // doubles between two ranks' slots
-    int64_t buf_stride;        // doubles between the two parity buffers
+    ulonglong2* const* gather;  // device array [world]: every rank's gather buffer (peer-mapped)
+    const long long* seq;       // this rank's step counter (device, 1 word); the step in flight is *seq + 1
+    int64_t slot_stride;        // LL elements between two ranks' slots
+    int64_t buf_stride;         // LL elements between the two parity buffers
     int rank, world;
 };
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void ll_store(ulonglong2* dst, double v, unsigned step) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long tag = (unsigned long long)step << 32;
+    const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-    long long v;
-    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ ulonglong2 ll_load(const ulonglong2* src) {
+    ulonglong2 w;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(src) : "memory");
+    return w;
+}
+__device__ __forceinline__ bool ll_ready(const ulonglong2& w, unsigned step) {
+    return (unsigned)(w.x >> 32) == step && (unsigned)(w.y >> 32) == step;
+}
+__device__ __forceinline__ double ll_value(const ulonglong2& w) {
+    return __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
 }

@@ -257,24 +257,23 @@ extern "C" int impala_mlp_backward_pair_push(const float* x, const float* params
                                              int64_t workspace_pi_bytes, void* workspace_vf,
                                              int64_t workspace_vf_bytes, int M_pi, int M_vf, int O, int H_pi,
                                              int H_vf, int A, const double* extra, int n_extra,
-                                             double* const* peer_gather, long long* const* peer_flags,
-                                             const long long* seq, int64_t slot_stride, int64_t buf_stride,
-                                             int rank, int world, void* stream) {
+                                             void* const* peer_gather, const long long* seq,
+                                             int64_t slot_stride, int64_t buf_stride, int rank, int world,
+                                             void* stream) {
     if (!x || !params_pi || !params_vf || !dlogits || !dv || !workspace_pi || !workspace_vf || !peer_gather ||
-        !peer_flags || !seq || (n_extra > 0 && !extra))
+        !seq || (n_extra > 0 && !extra))
         return IMPALA_ERR_BAD_ARG;
     if (world < 1 || world > 8 || rank < 0 || rank >= world || n_extra < 0 || n_extra > 32) return IMPALA_ERR_BAD_ARG;
     if (!impala_mlp_backward_pair_push_supported(M_pi, M_vf, O, H_pi, H_vf, A) ||
         !impala_mlp_bwd_tc_eligible(x, dlogits, M_pi, O, H_pi, A) || !impala_mlp_bwd_tc_eligible(x, dv, M_vf, O, H_vf, 1))
         return IMPALA_ERR_UNSUPPORTED_SHAPE;
     const int64_t n_pi = impala_make_layout(O, H_pi, A).total, n_vf = impala_make_layout(O, H_vf, 1).total;
-    if ((slot_stride & 1) || slot_stride < n_pi + n_vf + n_extra || buf_stride < (int64_t)world * slot_stride)
-        return IMPALA_ERR_BAD_ARG;
+    if (slot_stride < n_pi + n_vf + n_extra || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
     const int64_t need_pi = impala_mlp_backward_workspace(M_pi, O, H_pi, A);
     const int64_t need_vf = impala_mlp_backward_workspace(M_vf, O, H_vf, 1);
     if (need_pi < 0 || need_vf < 0) return IMPALA_ERR_UNSUPPORTED_SHAPE;
     if (workspace_pi_bytes < need_pi || workspace_vf_bytes < need_vf) return IMPALA_ERR_WORKSPACE_TOO_SMALL;
-    const PushArgs push{peer_gather, peer_flags, seq, slot_stride, buf_stride, rank, world};
+    const PushArgs push{reinterpret_cast<ulonglong2* const*>(peer_gather), seq, slot_stride, buf_stride, rank, world};
     return impala_mlp_bwd_tc_pair(
         x, params_pi, params_vf, dlogits, dv,
         reinterpret_cast<float*>(static_cast<char*>(workspace_pi) + kWsHeader),

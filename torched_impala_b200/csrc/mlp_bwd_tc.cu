@@ -479,28 +479,18 @@ __device__ __forceinline__ void grid_arrive_and_wait(unsigned int* ctl) {
     __syncthreads();
 }
 
-// The last CTA out re-arms the barrier for the next launch.  With `push` (data-parallel learner,
-// see optim.cu): every CTA's peer stores are fenced at system scope before it counts itself out,
-// and the last CTA out then releases this rank's "step s contribution complete" flag on every rank.
-__device__ __forceinline__ void grid_depart(unsigned int* ctl, const PushArgs* push = nullptr) {
-    if (threadIdx.x == 0) {
-        if (push) __threadfence_system();
-        if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
-            ctl[0] = 0u;
-            ctl[1] = 0u;
-            if (push) {
-                __threadfence_system();
-                const long long step = *push->seq + 1;
-                for (int r = 0; r < push->world; ++r) st_release_sys(push->flags[r] + push->rank, step);
-            }
-        }
+// The last CTA out re-arms the barrier for the next launch.
+__device__ __forceinline__ void grid_depart(unsigned int* ctl) {
+    if (threadIdx.x == 0 && atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+        ctl[0] = 0u;
+        ctl[1] = 0u;
     }
 }
 
 // Deterministic float64 sum of `nparts` partial rows: chunk c = entries [64c, 64c + 64); this CTA
 // takes chunks first, first + stride, ...; warp w adds rows w, w + kWarps, ... and warp 0 combines.
 // `push`: the sums go to entry push_off + e of slot `rank` in every rank's gather buffer instead of
-// a.grad (posted peer stores; the all-reduce of the data-parallel learner starts here).
+// a.grad (posted, step-tagged peer stores; the all-reduce of the data-parallel learner starts here).
 __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts, const int first,
                                             const int stride, double* s_red, const PushArgs* push = nullptr,
                                             const int64_t push_off = 0) {
@@ -533,11 +523,13 @@ __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts
             double tx = 0.0, ty = 0.0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
-            if (push) {
-                const int64_t off = ((*push->seq + 1) & 1) * push->buf_stride + (int64_t)push->rank * push->slot_stride +
-                                    push_off + e0;
-                for (int r = 0; r < push->world; ++r)
-                    *reinterpret_cast<double2*>(push->gather[r] + off) = make_double2(tx, ty);
+            if (push) {  // LL stores (common.cuh): value + step tag, no fence, no flag
+                const long long step = *push->seq + 1;
+                const int64_t off = (step & 1) * push->buf_stride + (int64_t)push->rank * push->slot_stride + push_off + e0;
+                for (int r = 0; r < push->world; ++r) {
+                    ll_store(push->gather[r] + off, tx, (unsigned)step);
+                    ll_store(push->gather[r] + off + 1, ty, (unsigned)step);
+                }
             } else {
                 *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
             }
@@ -571,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tc_kernel(const __grid_co
 // the far end so that no CTA gets two chunks of each).  Uses the policy workspace's control words.
 // PUSH: data-parallel learner - the reduced gradient [policy | value fn] and `n_extra` local
 // scalars (the loss sums the V-trace kernel left at `extra`) go straight into every rank's gather
-// buffer and the last CTA posts the flags (protocol in optim.cu); nothing is written to a.grad.
+// buffer as step-tagged LL elements (protocol in optim.cu); nothing is written to a.grad.
 template <bool PUSH>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_constant__ BwdTcArgs a_vf,
@@ -589,13 +581,13 @@ mlp_bwd_tc_pair_kernel(const __grid_constant__ BwdTcArgs a_pi, const __grid_cons
     reduce_rows(a_vf, n_vf, (int)gridDim.x - 1 - (int)blockIdx.x, gridDim.x, reinterpret_cast<double*>(scratch), pp,
                 a_pi.lay.total);
     if (PUSH && blockIdx.x == gridDim.x / 2 && (int)threadIdx.x < n_extra) {
-        const int64_t off = ((*push.seq + 1) & 1) * push.buf_stride + (int64_t)push.rank * push.slot_stride +
-                            a_pi.lay.total + a_vf.lay.total + threadIdx.x;
+        const long long step = *push.seq + 1;
+        const int64_t off = (step & 1) * push.buf_stride + (int64_t)push.rank * push.slot_stride + a_pi.lay.total +
+                            a_vf.lay.total + threadIdx.x;
         const double val = extra[threadIdx.x];
-        for (int r = 0; r < push.world; ++r) push.gather[r][off] = val;
+        for (int r = 0; r < push.world; ++r) ll_store(push.gather[r] + off, val, (unsigned)step);
     }
-    if (PUSH) __syncthreads();  // this CTA's peer stores precede thread 0's system fence
-    grid_depart(a_pi.ctl, pp);
+    grid_depart(a_pi.ctl);
     dump_trace(a_pi, s_trace, t_barrier);
 }
 

@@ -123,33 +123,30 @@ clip_adam_kernel(float* __restrict__ params, const double* __restrict__ grad, fl
 
 
 // ---------------------------------------------------------------------------------------------
-// Data-parallel learners: one-shot all-reduce over NVLink peer memory, PUSH model.
+// Data-parallel learners: one-shot all-reduce over NVLink peer memory - PUSH, LL format.
 //
-// Every rank owns a gather buffer  G[2 parities][world slots][stride]  of float64 that the other
-// ranks of the node have mapped (CUDA IPC).  The producer of a rank's [gradient | extra scalars]
-// contribution - the reduction tail of the paired tensor-core backward kernel (mlp_bwd_tc.cu), or
-// peer_push_kernel below for shapes that kernel does not cover - STORES it into slot `rank` of every
-// rank's buffer (posted writes: nobody waits for an NVLink round trip), and the last CTA of that
-// producer then stores the step number into entry `rank` of every rank's flag block.  The
-// optimizer kernel of each rank waits until its OWN flag block shows this step for all ranks
-// (local polling), adds the `world` slots of its OWN buffer in rank order - every rank forms
-// bit-identical sums, so the replicas cannot drift - and runs the clip norms and Adam on the sum.
+// Every rank owns a gather buffer  G[2 parities][world slots][slot_stride]  of 16-byte LL elements
+// (common.cuh) that the other ranks of the node have mapped (CUDA IPC).  The producer of a rank's
+// float64 [gradient | extra scalars] contribution - the reduction tail of the paired tensor-core
+// backward kernel (mlp_bwd_tc.cu), or peer_push_kernel below for shapes that kernel does not cover
+// - STORES every value, tagged with the step number, into slot `rank` of every rank's buffer:
+// posted NVLink writes, nobody waits for a round trip, no fence, no flag.  The optimizer kernel of
+// each rank polls the `world` slots of its OWN buffer (local memory) until each element carries
+// the current step, adds them in rank order - every rank forms bit-identical sums, so the
+// replicas cannot drift - and runs the clip norms and Adam on the sum.  The data path costs one
+// NVLink one-way latency.
 //
-// Ordering: producer CTAs finish their peer stores, fence at system scope and count themselves
-// out on a device counter; the CTA that counts out last fences again and releases the flags
-// (st.release.sys).  Consumers acquire the flags (ld.acquire.sys) before touching the slots.
-// The buffers are double-buffered by step parity, which makes a second "I have read your slot"
-// round trip unnecessary: a rank overwrites parity s & 1 in the backward of step s + 2, i.e. after
-// its optimizer kernel of step s + 1 saw every peer's flag for s + 1 - and a peer posts that flag
-// only at the end of a backward that runs after its optimizer kernel of step s (the one that read
+// The buffers are double-buffered by step parity, which makes an "I have read your slot" message
+// unnecessary: a rank overwrites parity s & 1 in the backward of step s + 2, i.e. after its
+// optimizer kernel of step s + 1 consumed every peer's step-(s + 1) values - and a peer sends
+// those only from a backward that runs after its optimizer kernel of step s (the one that read
 // the slots) has finished.  The step number lives in device memory (`seq`, advanced by the
-// optimizer kernel), so both kernels derive the parity themselves and ONE captured CUDA graph
-// serves every step.
+// optimizer kernel), so producer and consumer derive parity and tag themselves and ONE captured
+// CUDA graph serves every step.
 //
-// A rank that never arrives (its host is stuck) does not kill the others' CUDA contexts: after
+// A rank that never delivers (its host is stuck) does not kill the others' CUDA contexts: after
 // `timeout_ns` of polling the optimizer kernel sets an error word, leaves parameters, optimizer
 // state and `seq` untouched and exits normally; the host raises when it reads the word.
-// Flag block of a rank: int64[world], entry r written by rank r; monotonically increasing.
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -158,54 +155,43 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 constexpr int kPushCtas = 16, kPushThreads = 256;
 
-// Stand-alone producer: local[0, n) -> slot `rank` of every rank's gather buffer, then the flags.
-// ctl: one zeroed word (CTA count-out), re-armed by the last CTA.
+// Stand-alone producer: local[0, n) -> slot `rank` of every rank's gather buffer.
 __global__ void __launch_bounds__(kPushThreads)
-peer_push_kernel(const double* __restrict__ local, int64_t n, PushArgs p, unsigned int* ctl) {
+peer_push_kernel(const double* __restrict__ local, int64_t n, PushArgs p) {
     pdl_launch_dependents();
     pdl_wait();  // `local` comes from the backward kernel
     const long long step = *p.seq + 1;
     const int64_t off = (step & 1) * p.buf_stride + (int64_t)p.rank * p.slot_stride;
-    const int64_t n2 = n >> 1;  // double2 granularity (n is padded to an even count by the caller)
-    for (int64_t i = (int64_t)blockIdx.x * kPushThreads + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kPushThreads) {
-        const double2 v = reinterpret_cast<const double2*>(local)[i];
+    for (int64_t i = (int64_t)blockIdx.x * kPushThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kPushThreads) {
+        const double v = local[i];
 #pragma unroll 8
-        for (int r = 0; r < p.world; ++r) reinterpret_cast<double2*>(p.gather[r] + off)[i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(ctl, 1u) == gridDim.x - 1) {
-            *ctl = 0u;
-            __threadfence_system();
-            for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + p.rank, step);
-        }
+        for (int r = 0; r < p.world; ++r) ll_store(p.gather[r] + off + i, v, (unsigned)step);
     }
 }
 
-// Consumer: wait for every rank's flag, add the slots in rank order, clip + Adam.
+// Consumer: poll the local slots, add them in rank order, clip + Adam.
 __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(kAdamThreads)
 gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced,
-                        const double* __restrict__ gather, const long long* __restrict__ flags,
-                        long long* __restrict__ seq, int64_t slot_stride, int64_t buf_stride, int world,
-                        int n_extra, float* __restrict__ m, float* __restrict__ v,
-                        int64_t* __restrict__ state, int64_t n_policy, int64_t n_total, float max_norm,
-                        float lr, float beta1, float beta2, float eps, double* __restrict__ norms_out,
-                        int* __restrict__ err, unsigned long long timeout_ns) {
+                        const ulonglong2* __restrict__ gather, long long* __restrict__ seq,
+                        int64_t slot_stride, int64_t buf_stride, int world, int n_extra,
+                        float* __restrict__ m, float* __restrict__ v, int64_t* __restrict__ state,
+                        int64_t n_policy, int64_t n_total, float max_norm, float lr, float beta1,
+                        float beta2, float eps, double* __restrict__ norms_out, int* __restrict__ err,
+                        unsigned long long timeout_ns) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double s_warp[2][kAdamThreads / 32];
     __shared__ double s_cta[2];
-    __shared__ int s_abort;     // this CTA gave up waiting (read by the peers of the cluster)
+    __shared__ int s_abort;     // a thread of this CTA gave up waiting (read by the peers of the cluster)
+    __shared__ int s_any_abort;
     __shared__ float s_coef[2];
     __shared__ float s_bias[2];
     __shared__ double s_pow[2];
-    __shared__ long long s_step;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crank = (int)cluster.block_rank();
     const int64_t first = (int64_t)crank * kAdamThreads + tid;
     const int64_t stride = (int64_t)kAdamCluster * kAdamThreads;
 
-    // optimizer state that does not depend on the peers: issued before the wait
+    // optimizer state that does not depend on the peers: issued before anything else
     constexpr int kKeep = 2, kMaxWorld = 8;  // one NVLink node
     float pk[kKeep], mk[kKeep], vk[kKeep];
 #pragma unroll
@@ -215,24 +201,7 @@ gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced
         mk[k] = i < n_total ? m[i] : 0.f;
         vk[k] = i < n_total ? v[i] : 0.f;
     }
-    pdl_wait();  // flags / slots of this rank's own contribution come from the backward (or push) kernel
-    if (warp == 0) {
-        const long long step = *seq + 1;
-        int gave_up = 0;
-        if (lane < world) {  // lane r polls rank r's entry of the local flag block
-            const unsigned long long t0 = global_ns();
-            unsigned spins = 0;
-            while (ld_acquire_sys(flags + lane) < step) {
-                if ((++spins & 63u) == 0 && global_ns() - t0 > timeout_ns) {
-                    gave_up = 1;
-                    break;
-                }
-                __nanosleep(32);
-            }
-        }
-        gave_up = __any_sync(IMPALA_FULL_MASK, gave_up);
-        if (lane == 0) s_step = step, s_abort = gave_up;
-    }
+    if (tid == 0) s_abort = 0;
     if (tid == 64) {  // bias corrections from the running powers (nobody writes state before the end)
         const double p1 = state[0] == 0 ? 1.0 : __longlong_as_double(state[1]);
         const double p2 = state[0] == 0 ? 1.0 : __longlong_as_double(state[2]);
@@ -240,41 +209,57 @@ gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced
         s_bias[0] = (float)((double)lr / (1.0 - s_pow[0]));
         s_bias[1] = (float)(1.0 / sqrt(1.0 - s_pow[1]));
     }
+    pdl_wait();  // orders this kernel behind the local backward (its successors rely on that)
+    const long long step64 = *seq + 1;
+    const unsigned step = (unsigned)step64;
     __syncthreads();
 
-    // rank-ordered sums of this thread's entries: all local loads, independent of each other
-    const double* gb = gather + (s_step & 1) * buf_stride;
+    // rank-ordered sum of entry i: all `world` loads are issued together, then each is re-polled
+    // until it carries this step's tag (local memory: the peers' values arrive by themselves)
+    const ulonglong2* gb = gather + (step64 & 1) * buf_stride;
+    const unsigned long long t_start = global_ns();
+    bool ok = true;
     auto gsum = [&](int64_t i) {
-        double c[kMaxWorld];
+        ulonglong2 w[kMaxWorld];
 #pragma unroll
         for (int r = 0; r < kMaxWorld; ++r)
-            if (r < world) c[r] = __ldcg(gb + r * slot_stride + i);
+            if (r < world) w[r] = ll_load(gb + r * slot_stride + i);
         double s = 0.0;
 #pragma unroll
-        for (int r = 0; r < kMaxWorld; ++r)
-            if (r < world) s += c[r];
+        for (int r = 0; r < kMaxWorld; ++r) {
+            if (r < world) {
+                unsigned spins = 0;
+                while (!ll_ready(w[r], step)) {
+                    if ((++spins & 255u) == 0 && global_ns() - t_start > timeout_ns) {
+                        ok = false;
+                        break;
+                    }
+                    if (spins > 16) __nanosleep(20);
+                    w[r] = ll_load(gb + r * slot_stride + i);
+                }
+                s += ll_value(w[r]);
+            }
+        }
         return s;
     };
     double gk[kKeep];
     double ss0 = 0.0, ss1 = 0.0;
-    const bool go = !s_abort;
 #pragma unroll
     for (int k = 0; k < kKeep; ++k) {
         const int64_t i = first + k * stride;
-        gk[k] = (go && i < n_total) ? gsum(i) : 0.0;
-        if (go && i < n_total) reduced[i] = gk[k];
+        gk[k] = i < n_total ? gsum(i) : 0.0;
+        if (i < n_total) reduced[i] = gk[k];
         if (i < n_policy) ss0 += gk[k] * gk[k];
         else ss1 += gk[k] * gk[k];
     }
-    if (go) {
-        for (int64_t i = first + kKeep * stride; i < n_total; i += stride) {
-            const double g = gsum(i);
-            reduced[i] = g;
-            if (i < n_policy) ss0 += g * g;
-            else ss1 += g * g;
-        }
-        if (crank == 0 && tid < n_extra) reduced[n_total + tid] = gsum(n_total + tid);  // logged scalars
+    for (int64_t i = first + kKeep * stride; i < n_total; i += stride) {
+        const double g = gsum(i);
+        reduced[i] = g;
+        if (i < n_policy) ss0 += g * g;
+        else ss1 += g * g;
     }
+    if (crank == 0 && tid < n_extra) reduced[n_total + tid] = gsum(n_total + tid);  // logged scalars
+    if (!ok) s_abort = 1;
     ss0 = warp_sum_f64(ss0);
     ss1 = warp_sum_f64(ss1);
     if (lane == 0) s_warp[0][warp] = ss0, s_warp[1][warp] = ss1;
@@ -285,7 +270,6 @@ gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced
         s_cta[tid] = s;
     }
     cluster.sync();  // all 8 partial pairs (and abort flags) are in place
-    __shared__ int s_any_abort;
     if (tid == 0) {
         int ab = 0;
         for (int r = 0; r < kAdamCluster; ++r) ab |= *cluster.map_shared_rank(&s_abort, r);
@@ -327,7 +311,7 @@ gather_clip_adam_kernel(float* __restrict__ params, double* __restrict__ reduced
             state[0] += 1;
             state[1] = __double_as_longlong(s_pow[0]);
             state[2] = __double_as_longlong(s_pow[1]);
-            *seq = s_step;
+            *seq = step64;
         }
     }
 }
@@ -346,34 +330,33 @@ extern "C" int impala_clip_adam(float* params, const double* grad, float* m, flo
     return impala_launch_status();
 }
 
-extern "C" int impala_peer_push(const double* local, int64_t n, double* const* peer_gather,
-                                long long* const* peer_flags, const long long* seq, int64_t slot_stride,
-                                int64_t buf_stride, int rank, int world, unsigned int* ctl, void* stream) {
-    if (!local || !peer_gather || !peer_flags || !seq || !ctl) return IMPALA_ERR_BAD_ARG;
-    if (n < 2 || (n & 1) || world < 1 || world > 8 || rank < 0 || rank >= world) return IMPALA_ERR_BAD_ARG;
-    if (slot_stride < n || (slot_stride & 1) || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
-    if ((reinterpret_cast<uintptr_t>(local) & 15) != 0) return IMPALA_ERR_BAD_ARG;
-    PushArgs p{peer_gather, peer_flags, seq, slot_stride, buf_stride, rank, world};
-    const cudaError_t e = impala_launch(peer_push_kernel, kPushCtas, kPushThreads, 0, (cudaStream_t)stream, true, local, n, p, ctl);
+extern "C" int impala_peer_push(const double* local, int64_t n, void* const* peer_gather, const long long* seq,
+                                int64_t slot_stride, int64_t buf_stride, int rank, int world, void* stream) {
+    if (!local || !peer_gather || !seq) return IMPALA_ERR_BAD_ARG;
+    if (n < 1 || world < 1 || world > 8 || rank < 0 || rank >= world) return IMPALA_ERR_BAD_ARG;
+    if (slot_stride < n || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
+    PushArgs p{reinterpret_cast<ulonglong2* const*>(peer_gather), seq, slot_stride, buf_stride, rank, world};
+    const cudaError_t e = impala_launch(peer_push_kernel, kPushCtas, kPushThreads, 0, (cudaStream_t)stream, true, local, n, p);
     if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
-extern "C" int impala_gather_clip_adam(float* params, double* reduced, const double* gather,
-                                       const long long* flags, long long* seq, int64_t slot_stride,
-                                       int64_t buf_stride, int world, int n_extra, float* m, float* v,
-                                       int64_t* state, int64_t n_policy, int64_t n_total, float max_norm,
-                                       float lr, float beta1, float beta2, float eps, double* norms_out,
-                                       int* err, double timeout_s, void* stream) {
-    if (!params || !reduced || !gather || !flags || !seq || !m || !v || !state) return IMPALA_ERR_BAD_ARG;
+extern "C" int impala_gather_clip_adam(float* params, double* reduced, const void* gather, long long* seq,
+                                       int64_t slot_stride, int64_t buf_stride, int world, int n_extra, float* m,
+                                       float* v, int64_t* state, int64_t n_policy, int64_t n_total, float max_norm,
+                                       float lr, float beta1, float beta2, float eps, double* norms_out, int* err,
+                                       double timeout_s, void* stream) {
+    if (!params || !reduced || !gather || !seq || !m || !v || !state) return IMPALA_ERR_BAD_ARG;
     if (n_total < 1 || n_policy < 0 || n_policy > n_total) return IMPALA_ERR_BAD_ARG;
     if (world < 1 || world > 8 || n_extra < 0 || n_extra > kAdamThreads) return IMPALA_ERR_BAD_ARG;
     if (slot_stride < n_total + n_extra || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(gather) & 15) return IMPALA_ERR_BAD_ARG;
     const unsigned long long timeout_ns =
         timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 600ull * 1000000000ull;
     const cudaError_t e = impala_launch(gather_clip_adam_kernel, kAdamCluster, kAdamThreads, 0, (cudaStream_t)stream, true,
-                                        params, reduced, gather, flags, seq, slot_stride, buf_stride, world, n_extra, m, v,
-                                        state, n_policy, n_total, max_norm, lr, beta1, beta2, eps, norms_out, err, timeout_ns);
+                                        params, reduced, static_cast<const ulonglong2*>(gather), seq, slot_stride, buf_stride,
+                                        world, n_extra, m, v, state, n_policy, n_total, max_norm, lr, beta1, beta2, eps,
+                                        norms_out, err, timeout_ns);
     if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }

@@ -12,9 +12,9 @@ include/impala_b200.h (PyTorch only provides device memory, streams and
     impala_clip_adam           per-net clip + Adam + step counter               learner.py:176-183
       N > 1 (new): the all-reduce of [grads | scalars] is a PUSH over NVLink peer memory -
       the tail of impala_mlp_backward_pair_push (or impala_peer_push for shapes it does not cover)
-      stores this rank's contribution into every rank's gather buffer and posts a flag;
-      impala_gather_clip_adam waits for the local flags, adds the local slots in rank order and
-      applies the update.  IMPALA_ALLREDUCE=nccl: torch.distributed all-reduce between the
+      stores this rank's contribution, every value tagged with the step number (LL format), into
+      every rank's gather buffer; impala_gather_clip_adam polls its local slots, adds them in rank
+      order and applies the update.  IMPALA_ALLREDUCE=nccl: torch.distributed all-reduce between the
       backward and impala_clip_adam instead.
 
 With `use_graph=True` the whole launch sequence of a step is captured once per slab into ONE CUDA
@@ -139,8 +139,8 @@ class LearnerEngine:
     # ------------------------------------------------------------------ parameters
     # ------------------------------------------------------------------------ multi-GPU plumbing
     def _setup_peer_allreduce(self) -> None:
-        """Allocate this rank's gather buffer and flag block, map every peer's (CUDA IPC over NVLink)
-        for the push-model all-reduce.  IMPALA_ALLREDUCE=nccl - or a failed mapping on ANY rank -
+        """Allocate this rank's gather buffer (LL elements, 16 bytes per float64) and map every peer's
+        (CUDA IPC over NVLink) for the push-model all-reduce.  IMPALA_ALLREDUCE=nccl - or a failed mapping on ANY rank -
         keeps the torch.distributed all-reduce between the backward and the optimizer instead."""
         import os
         import warnings
@@ -150,11 +150,11 @@ class LearnerEngine:
         rank, world = dist.get_rank(self.pg), self.world
         ok, err, mine = os.environ.get("IMPALA_ALLREDUCE", "peer") != "nccl" and world <= 8, "", {}
         lib = self.lib
-        slot = (self.n_total + 8 + 1) // 2 * 2          # doubles per rank slot: [gradient | scalars | pad], even
-        buf = world * slot                              # doubles per parity buffer
+        slot = self.n_total + 8                         # LL elements per rank slot: [gradient | scalars | pad]
+        buf = world * slot                              # LL elements per parity buffer
         if ok:
             try:
-                for name, nbytes in (("gather", 2 * 8 * buf), ("flags", 8 * world)):
+                for name, nbytes in (("gather", 2 * 16 * buf),):
                     ptr, handle = C.c_void_p(), (C.c_char * 64)()
                     _cabi.check(lib.impala_peer_alloc(nbytes, C.byref(ptr), handle), "impala_peer_alloc")
                     mine[name] = (ptr.value, bytes(handle.raw))
@@ -163,12 +163,12 @@ class LearnerEngine:
         handles = [None] * world
         dist.all_gather_object(handles, {k: v[1] for k, v in mine.items()} if ok else None, group=self.pg)
         ok = ok and all(h is not None for h in handles)
-        ptrs = {"gather": [], "flags": []}
+        ptrs = {"gather": []}
         opened = []
         if ok:
             try:
                 for r, h in enumerate(handles):
-                    for name in ("gather", "flags"):
+                    for name in ("gather",):
                         if r == rank:
                             ptrs[name].append(mine[name][0])
                         else:
@@ -189,10 +189,8 @@ class LearnerEngine:
         fused = bool(lib.impala_mlp_backward_pair_push_supported(self.M_pi, self.M_vf, self.O, self.H_pi, self.H_v, self.A))
         if os.environ.get("IMPALA_PUSH_FUSED", "1") == "0":
             fused = False
-        self.peer = dict(gather=mine["gather"][0], flags=mine["flags"][0], opened=opened,
-                         gather_ptrs=torch.tensor(ptrs["gather"], **i64), flag_ptrs=torch.tensor(ptrs["flags"], **i64),
+        self.peer = dict(gather=mine["gather"][0], opened=opened, gather_ptrs=torch.tensor(ptrs["gather"], **i64),
                          seq=torch.zeros(1, **i64), rank=rank, slot=slot, buf=buf, fused=fused,
-                         ctl=torch.zeros(4, dtype=torch.int32, device=self.dev),
                          err=torch.zeros(1, dtype=torch.int32, device=self.dev),
                          timeout_s=float(os.environ.get("IMPALA_PEER_TIMEOUT_S", "600")))
         torch.cuda.synchronize(self.dev)
@@ -331,17 +329,17 @@ class LearnerEngine:
             _cabi.check(lib.impala_mlp_backward_pair_push(
                 obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), _ptr(self.ws_pi), self.ws_pi_bytes,
                 _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, scal, 4,
-                _ptr(pr["gather_ptrs"]), _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"],
-                self.world, st), "impala_mlp_backward_pair_push")
+                _ptr(pr["gather_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"], self.world, st),
+                "impala_mlp_backward_pair_push")
         else:
             _cabi.check(lib.impala_mlp_backward_pair(
                 obs, p_pi, p_vf, _ptr(self.dlogits), _ptr(self.dv), g_pi, g_vf, _ptr(self.ws_pi), self.ws_pi_bytes,
                 _ptr(self.ws_vf), self.ws_vf_bytes, self.M_pi, self.M_vf, O, self.H_pi, self.H_v, A, st),
                 "impala_mlp_backward_pair")
-            if pr:  # stand-alone producer: comm[0 : n_total + 8) -> every rank's gather buffer, then the flags
+            if pr:  # stand-alone producer: comm[0 : n_total + 8) -> every rank's gather buffer
                 _cabi.check(lib.impala_peer_push(_ptr(self.comm), self.n_total + 8, _ptr(pr["gather_ptrs"]),
-                                                 _ptr(pr["flag_ptrs"]), _ptr(pr["seq"]), pr["slot"], pr["buf"],
-                                                 pr["rank"], self.world, _ptr(pr["ctl"]), st), "impala_peer_push")
+                                                 _ptr(pr["seq"]), pr["slot"], pr["buf"], pr["rank"], self.world, st),
+                            "impala_peer_push")
         return int(lib.impala_launch_count() - launched)  # kernels actually launched / captured
 
     def _enqueue_opt(self) -> int:
@@ -349,7 +347,7 @@ class LearnerEngine:
         if self.peer:
             pr = self.peer
             _cabi.check(self.lib.impala_gather_clip_adam(
-                _ptr(self.params), _ptr(self.comm), C.c_void_p(pr["gather"]), C.c_void_p(pr["flags"]), _ptr(pr["seq"]),
+                _ptr(self.params), _ptr(self.comm), C.c_void_p(pr["gather"]), _ptr(pr["seq"]),
                 pr["slot"], pr["buf"], self.world, 4, _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.adam_step),
                 self.n_pi, self.n_total, float(hp.max_norm), float(0.95 * hp.lr), 0.9, 0.999, 1e-8,
                 _ptr(self.norms), _ptr(pr["err"]), pr["timeout_s"], st), "impala_gather_clip_adam")
