@@ -186,6 +186,28 @@ def run_reference_arm(args):
     emit(reference_line(args, cb, steps, warm))
 
 
+def learner_e2e(config: str, devices: int):
+    """The same metric THROUGH the product API: forked `Learner(devices=N)` behind a `RingQueue` fed by
+    32 synthetic actor processes (scripts/learner_e2e.py, fresh interpreter - this process has CUDA
+    initialised and must not fork a CUDA child).  Includes queue -> slab packing in the actors, the
+    per-rank shard DMAs, the update and the weight publication."""
+    if config not in ("c3", "c4"):
+        return None
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "learner_e2e.py"), "--config", config, "--actors", "32",
+           "--updates", "600", "--warmup", "100", "--devices", str(devices), "--deadline", "90"]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+        for ln in reversed(res.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return dict(error="no JSON line", stderr=res.stderr[-500:])
+    except subprocess.TimeoutExpired:
+        return dict(error="timed out")
+
+
 def cpu_baseline(config: str):
     """`cpu_baseline` of the own arm: the reference arm in a fresh CPU-only subprocess (this process
     has CUDA initialised; the reference resolves its device at import), 1 + 3 updates."""
@@ -623,6 +645,7 @@ def run_own_arm(args):
             dist.destroy_process_group()
         return
     cb = cpu_baseline(args.config) if world == 1 and not args.no_cpu else None
+    e2e_learner = learner_e2e(args.config, world) if not args.no_learner else None
     ms = dev_ms / args.steps
     line = dict(
         metric=METRIC, value=1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps,
@@ -646,6 +669,8 @@ def run_own_arm(args):
     )
     if weak:
         line["weak_scaling"] = weak
+    if e2e_learner:
+        line["e2e_learner"] = e2e_learner
     if cb:
         line["cpu_baseline"] = cb
     emit(line)
@@ -673,6 +698,7 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS), help="BASELINE.json config (default: c4, the metric's)")
     ap.add_argument("--no-parity", action="store_true", help="skip the first-step oracle check")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
+    ap.add_argument("--no-learner", action="store_true", help="skip the run through Learner + RingQueue + actor processes")
     args = ap.parse_args()
     select_workload(args.config)
     if args.impl == "reference":

@@ -66,6 +66,7 @@ def main():
     a = ap.parse_args()
     w = CFG[a.config]
     mp.set_start_method("fork", force=True)
+    os.environ.setdefault("IMPALA_DEBUG_STACKS", "25")  # a stuck learner shows where
     hp = default_hparams(batch_size=w["B"], max_timesteps=w["T"], policy_hidden_dims=w["H"], value_fn_hidden_dims=w["H"],
                          max_updates=a.updates, verbose=0, eval_every=None, save_every=10 ** 9, n_actors=a.actors)
     policy, value_fn = MlpPolicy(w["O"], w["A"], w["H"]), MlpValueFn(w["O"], w["H"])

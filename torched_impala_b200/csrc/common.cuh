@@ -79,15 +79,19 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
     return x;
 }
 
-// ---- programmatic dependent launch (PDL): the kernels of a learner step are launched so that
-// kernel k + 1 may be scheduled while kernel k is still running: each kernel calls
-// pdl_launch_dependents() first thing (its successor may start occupying free SM resources and
-// run its own prologue - barrier init, TMEM allocation, weight staging, optimizer-state loads)
-// and pdl_wait() before the first access to anything its predecessor produces (returns at once
-// when the launch had no programmatic predecessor).  Inside a captured CUDA graph these become
-// programmatic edges.  IMPALA_PDL=0 restores plain stream-ordered launches.
+// ---- programmatic dependent launch (PDL): kernels 2..4 of a learner step are launched with the
+// programmatic-stream-serialization attribute and call pdl_wait() before the first access to
+// anything their predecessor produces.  No kernel triggers early (no griddepcontrol.launch_dependents):
+// the trigger is the implicit one at the exit of each predecessor CTA, i.e. every write of the
+// predecessor precedes it, so the successor's CTAs are merely pre-staged - they occupy SMs as the
+// predecessor's CTAs drain and run their own prologue (barrier init, TMEM allocation, weight
+// staging, optimizer-state loads) while the last predecessor CTAs finish - and pdl_wait()
+// returns once the predecessor grid is complete and flushed.  (An early trigger at kernel start
+// was measured first: the optimizer then read gradients the backward's reduction phase had not
+// written yet - tests/test_gpu_fullsize.py caught it - so the wait must not be relied on to cover
+// writes issued after a trigger.)  Inside a captured CUDA graph these launches become programmatic
+// edges.  IMPALA_PDL=0 restores plain stream-ordered launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,

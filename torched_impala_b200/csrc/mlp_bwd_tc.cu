@@ -111,7 +111,6 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     Barriers* bars = reinterpret_cast<Barriers*>(exch + (NP + 1) * 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_launch_dependents();  // the optimizer kernel may be scheduled (and load its state) meanwhile
     const float* __restrict__ W1 = a.params + a.lay.oW1;
     const float* __restrict__ b1 = a.params + a.lay.ob1;
     const float* __restrict__ W2 = a.params + a.lay.oW2;

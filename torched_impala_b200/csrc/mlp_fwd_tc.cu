@@ -74,7 +74,6 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
     Barriers* bars = reinterpret_cast<Barriers*>(part + 2 * 3 * kTileM * NP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_launch_dependents();  // the next kernel of the step may be scheduled as SMs free up (common.cuh)
     const bool tr = a.trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 20);
 #define TRACE(tile, ev)                                              \
     if (tr && (tile) < 24) s_trace[(tile) * 16 + (ev)] = clock64();

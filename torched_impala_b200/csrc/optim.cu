@@ -158,7 +158,6 @@ constexpr int kPushCtas = 16, kPushThreads = 256;
 // Stand-alone producer: local[0, n) -> slot `rank` of every rank's gather buffer.
 __global__ void __launch_bounds__(kPushThreads)
 peer_push_kernel(const double* __restrict__ local, int64_t n, PushArgs p) {
-    pdl_launch_dependents();
     pdl_wait();  // `local` comes from the backward kernel
     const long long step = *p.seq + 1;
     const int64_t off = (step & 1) * p.buf_stride + (int64_t)p.rank * p.slot_stride;

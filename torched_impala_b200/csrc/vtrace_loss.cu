@@ -126,7 +126,6 @@ template <int AP, int S, int MAXT, int MINB, bool WITH_LOSS, bool VEC>
 __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a) {
     __shared__ float2 s_map[2][kMaxSeg][32];
     __shared__ double s_red[kMaxSeg][4];
-    pdl_launch_dependents();
     pdl_wait();  // logits / values come from the forward kernel
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nseg = blockDim.x >> 5;
     const int T = a.T, B = a.B, A = VEC ? AP : a.A;
@@ -350,9 +349,7 @@ int launch_s(const VtArgs& a, bool vec, unsigned grid, int nseg, cudaStream_t st
     return impala_launch_status();
 }
 
-// Steps per thread (S) and segments per CTA: short unrolls get S = 2 (as many threads as possible,
-// the launch is latency bound), long ones S = 5 with up to 10 segments (50 steps per chunk,
-// 320-thread CTAs, two resident per SM); wide action sets trade S for registers.
+// Steps per thread (S) and segments (warps) per CTA; wide action sets trade S for registers.
 // IMPALA_VTRACE_S / IMPALA_VTRACE_NSEG override the choice (tuning).
 template <bool WITH_LOSS>
 int launch(VtArgs& a, cudaStream_t st) {
@@ -364,12 +361,14 @@ int launch(VtArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.B + 31) / 32);
     const bool vec = a.A == AP && aligned16(a.cur_logits) && aligned16(a.beh_logits) &&
                      (!WITH_LOSS || aligned16(a.dlogits));
-    int S = AP == 16 ? 1 : (AP == 8 || a.T <= 32 ? 2 : 5);
+    // measured on B200 (scripts/tune_vtrace.py): S = 2 wins at every unroll; all steps in one chunk up to
+    // 10 segments (T <= 20), otherwise 8 segments (16 steps per chunk, next chunk prefetched)
+    int S = AP == 16 ? 1 : 2;
     const int s_env = impala_env_int("IMPALA_VTRACE_S", 0);
     if (AP <= 4 && (s_env == 2 || s_env == 5)) S = s_env;
     const int max_seg = S == 5 ? 10 : kMaxSeg;
     int nseg = (a.T + S - 1) / S;
-    if (nseg > max_seg) nseg = max_seg;
+    if (nseg > 10) nseg = 8;
     const int n_env = impala_env_int("IMPALA_VTRACE_NSEG", 0);
     if (n_env >= 1 && n_env <= max_seg) nseg = n_env;
     if (AP == 2) return S == 5 ? launch_s<2, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st)

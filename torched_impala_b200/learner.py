@@ -390,6 +390,13 @@ class Learner:
         """Process target (learner.py:67): loop until the shared counter reaches max_updates."""
         writer, pub, leader, eng = None, None, None, None
         try:
+            import os
+
+            if os.environ.get("IMPALA_DEBUG_STACKS"):  # dump every thread's stack if the process is still alive then
+                import faulthandler
+                import sys
+
+                faulthandler.dump_traceback_later(float(os.environ["IMPALA_DEBUG_STACKS"]), repeat=True, file=sys.stderr)
             self._restore_gpu_visibility()
             world = len(self.devices)
             ring = self.q if hasattr(self.q, "collect_batch") else None  # ring.RingQueue (SURVEY 8f-1)
