@@ -47,9 +47,9 @@ def main():
                  ws=torch.zeros(int(lib.impala_vtrace_loss_workspace(T, B, A)), dtype=torch.uint8, device="cuda"))
         by_in = 4 * T * B * (2 * A + 2) + T * B + 4 * (T + 1) * B
         by = by_in + 4 * (T + 1) * B + 4 * T * B + (4 * T * B * A + 4 * (T + 1) * B if loss else 0)
-        for S in (2, 5):
-            for nseg in ((4, 8, 10, 16) if S == 2 else (4, 5, 8, 10)):
-                if S * nseg < min(T, 10):
+        for S in (1, 2, 5):
+            for nseg in ({1: (8, 16, 20, 32), 2: (4, 8, 10, 16), 5: (4, 5, 8, 10)}[S]):
+                if S * nseg < min(T, 10) or (S == 1 and T > 32 and nseg != 32):
                     continue
                 os.environ["IMPALA_VTRACE_S"], os.environ["IMPALA_VTRACE_NSEG"] = str(S), str(nseg)
                 P = lambda t: C.c_void_p(t.data_ptr())

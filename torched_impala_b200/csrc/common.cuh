@@ -90,7 +90,9 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
 // was measured first: the optimizer then read gradients the backward's reduction phase had not
 // written yet - tests/test_gpu_fullsize.py caught it - so the wait must not be relied on to cover
 // writes issued after a trigger.)  Inside a captured CUDA graph these launches become programmatic
-// edges.  IMPALA_PDL=0 restores plain stream-ordered launches.
+// edges.  Measured on the B200 (c4, 100 steps): 84.9 us per step with the attribute, 84.3 us without -
+// without an early trigger there is nothing left to overlap, so the attribute is OFF by default
+// (IMPALA_PDL=1 enables it; the waits are no-ops on plain launches).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
@@ -100,7 +102,7 @@ static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     unsigned n = 0;
-    if (dependent && impala_env_int("IMPALA_PDL", 1) != 0) {
+    if (dependent && impala_env_int("IMPALA_PDL", 0) != 0) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         n = 1;

@@ -47,7 +47,7 @@ __device__ __forceinline__ float selp_f32(bool p, float x, float y) {
     return d;
 }
 
-constexpr int kMaxSeg = 16;  // time segments (= warps) per CTA
+constexpr int kMaxSeg = 32;  // time segments (= warps) per CTA
 
 struct VtArgs {
     const float* cur_logits;
@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(MAXT, MINB) vtrace_lane_kernel(const VtArgs a)
             for (int k = 1; k < AP; ++k)
                 if (k < A) mx = fmaxf(mx, R.zc[i][k]), mxb = fmaxf(mxb, R.zb[i][k]);
             float se = 0.f, seb = 0.f;
+            const float mxl = -mx * kLog2e, mxbl = -mxb * kLog2e;
 #pragma unroll
             for (int k = 0; k < AP; ++k) {
-                R.zc[i][k] = (R.zc[i][k] - mx) * kLog2e;
-                R.zb[i][k] = (R.zb[i][k] - mxb) * kLog2e;
+                R.zc[i][k] = fmaf(R.zc[i][k], kLog2e, mxl);   // (z - max) log2(e), one rounding
+                R.zb[i][k] = fmaf(R.zb[i][k], kLog2e, mxbl);
                 if (k < A) se += ex2f(R.zc[i][k]), seb += ex2f(R.zb[i][k]);
             }
             const float lse = lg2f(se), lseb = lg2f(seb);
@@ -361,20 +362,27 @@ int launch(VtArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.B + 31) / 32);
     const bool vec = a.A == AP && aligned16(a.cur_logits) && aligned16(a.beh_logits) &&
                      (!WITH_LOSS || aligned16(a.dlogits));
-    // measured on B200 (scripts/tune_vtrace.py): S = 2 wins at every unroll; all steps in one chunk up to
-    // 10 segments (T <= 20), otherwise 8 segments (16 steps per chunk, next chunk prefetched)
-    int S = AP == 16 ? 1 : 2;
+    // measured on B200 (scripts/tune_vtrace.py): short unrolls are latency bound - one step per thread,
+    // every step of the unroll in one chunk (T <= 32: T warps per CTA); long unrolls: S = 2, 8 segments
+    // (16 steps per chunk, next chunk prefetched, 3 CTAs per SM)
+    int S = AP == 16 ? 1 : (AP <= 4 && a.T <= kMaxSeg ? 1 : 2);
     const int s_env = impala_env_int("IMPALA_VTRACE_S", 0);
-    if (AP <= 4 && (s_env == 2 || s_env == 5)) S = s_env;
-    const int max_seg = S == 5 ? 10 : kMaxSeg;
+    if (AP <= 4 && (s_env == 1 || s_env == 2 || s_env == 5)) S = s_env;
+    const int max_seg = S == 5 ? 10 : (AP <= 4 ? kMaxSeg : 16);
     int nseg = (a.T + S - 1) / S;
-    if (nseg > 10) nseg = 8;
+    if (nseg > (S == 1 ? kMaxSeg : 10)) nseg = 8;
     const int n_env = impala_env_int("IMPALA_VTRACE_NSEG", 0);
     if (n_env >= 1 && n_env <= max_seg) nseg = n_env;
-    if (AP == 2) return S == 5 ? launch_s<2, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st)
-                               : launch_s<2, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
-    if (AP == 4) return S == 5 ? launch_s<4, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st)
-                               : launch_s<4, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
+#define VT_AP(APV)                                                                                      \
+    if (AP == APV) {                                                                                    \
+        if (S == 5) return launch_s<APV, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st);                 \
+        if (S == 1) return launch_s<APV, 1, 1024, 1, WITH_LOSS>(a, vec, grid, nseg, st);                \
+        return nseg <= 8 ? launch_s<APV, 2, 256, 3, WITH_LOSS>(a, vec, grid, nseg, st)                  \
+                         : launch_s<APV, 2, 1024, 1, WITH_LOSS>(a, vec, grid, nseg, st);                \
+    }
+    VT_AP(2)
+    VT_AP(4)
+#undef VT_AP
     if (AP == 8) return launch_s<8, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
     return launch_s<16, 1, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st);
 }

@@ -397,6 +397,10 @@ class Learner:
                 import sys
 
                 faulthandler.dump_traceback_later(float(os.environ["IMPALA_DEBUG_STACKS"]), repeat=True, file=sys.stderr)
+            # The forked child inherits the launcher's OpenMP state without its worker threads: the first
+            # multi-threaded CPU op (e.g. zero-filling a multi-megabyte pinned slab) would wait forever
+            # for them.  The learner's host work is tiny copies; one intra-op thread is also the fastest.
+            torch.set_num_threads(1)
             self._restore_gpu_visibility()
             world = len(self.devices)
             ring = self.q if hasattr(self.q, "collect_batch") else None  # ring.RingQueue
