@@ -127,7 +127,9 @@ __device__ __forceinline__ void ll_store(ulonglong2* dst, double v, unsigned ste
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     const unsigned long long tag = (unsigned long long)step << 32;
     const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+    // plain (weak) 16-byte store: LL needs no ordering between elements, only that each 8-byte half
+    // lands whole - which any aligned 8-byte store does
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
 }
 __device__ __forceinline__ ulonglong2 ll_load(const ulonglong2* src) {
     ulonglong2 w;

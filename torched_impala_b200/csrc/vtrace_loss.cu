@@ -362,10 +362,10 @@ int launch(VtArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.B + 31) / 32);
     const bool vec = a.A == AP && aligned16(a.cur_logits) && aligned16(a.beh_logits) &&
                      (!WITH_LOSS || aligned16(a.dlogits));
-    // measured on B200 (scripts/tune_vtrace.py): short unrolls are latency bound - one step per thread,
-    // every step of the unroll in one chunk (T <= 32: T warps per CTA); long unrolls: S = 2, 8 segments
-    // (16 steps per chunk, next chunk prefetched, 3 CTAs per SM)
-    int S = AP == 16 ? 1 : (AP <= 4 && a.T <= kMaxSeg ? 1 : 2);
+    // measured on B200 (scripts/tune_vtrace.py, ncu): S = 2 everywhere; every step of the unroll in one
+    // chunk up to 10 segments (T <= 20), otherwise 8 segments (16 steps per chunk, next chunk
+    // prefetched).  S = 1 (one step per thread, up to 32 warps) and S = 5 stay selectable.
+    int S = AP == 16 ? 1 : 2;
     const int s_env = impala_env_int("IMPALA_VTRACE_S", 0);
     if (AP <= 4 && (s_env == 1 || s_env == 2 || s_env == 5)) S = s_env;
     const int max_seg = S == 5 ? 10 : (AP <= 4 ? kMaxSeg : 16);
@@ -377,8 +377,8 @@ int launch(VtArgs& a, cudaStream_t st) {
     if (AP == APV) {                                                                                    \
         if (S == 5) return launch_s<APV, 5, 320, 1, WITH_LOSS>(a, vec, grid, nseg, st);                 \
         if (S == 1) return launch_s<APV, 1, 1024, 1, WITH_LOSS>(a, vec, grid, nseg, st);                \
-        return nseg <= 8 ? launch_s<APV, 2, 256, 3, WITH_LOSS>(a, vec, grid, nseg, st)                  \
-                         : launch_s<APV, 2, 1024, 1, WITH_LOSS>(a, vec, grid, nseg, st);                \
+        return nseg <= 16 ? launch_s<APV, 2, 512, 1, WITH_LOSS>(a, vec, grid, nseg, st)                 \
+                          : launch_s<APV, 2, 1024, 1, WITH_LOSS>(a, vec, grid, nseg, st);               \
     }
     VT_AP(2)
     VT_AP(4)
