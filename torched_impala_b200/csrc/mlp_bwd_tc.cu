@@ -4,12 +4,15 @@
 // Transposed formulation so that a thread owns a HIDDEN unit (TMEM lane = hidden unit), per tile
 // of 64 batch rows:
 //
-//   UMMA1 (SS, recompute)  PRE[H, 64]  = W1'[H, K'] * X'[64, K']^T   X' = [x | 0], W1' = [W1 | 0]
-//   CUDA cores             pre = PRE + b1; h = relu(pre); dh = W2^T dz; dW2 += dz h;
-//                          DP = (pre > 0) ? dh : 0;  db1 += DP
-//   UMMA2 (TS, reduction)  dW1'[H, K'] += DP[H, 64] * X'[64, K']
-// (b1 / db1 stay on the CUDA cores: folding them into K would cost a fourth K step of UMMA1 at
-// O = 24, i.e. a third more accumulator columns streamed, for one FADD per element.)
+//   UMMA1 (SS, recompute)  PRE[H, 64]  = W1'[H, K'] * X'[64, K']^T   X' = [x | 1 | 0], W1' = [W1 | b1 | 0]
+//   CUDA cores             h = relu(PRE); dh = W2^T dz; dW2 += dz h;  DP = (PRE > 0) ? dh : 0
+//   UMMA2 (TS, reduction)  dW1'[H, K'] += DP[H, 64] * X'[64, K']      column O of dW1' = db1
+// The bias rides in K (column O of X' is 1): the pre-activation arrives complete and db1 falls out
+// of the reduction GEMM for free.  The epilogue is bound by the FMA pipe (13 packed fp32 ops per
+// (row pair, hidden unit) in round 1: bias, two mask multiplies, dh, dW2, DP, db1, hi/lo split);
+// with the bias and db1 on the tensor cores and ReLU / ReLU' as FMNMX / FSEL on the ALU pipe, 9
+// remain (policy; 3 for the value net) - the fourth K step of UMMA1 at O = 24 is paid by a pipe
+// that is idle half of the time.
 //
 // PRE lands in TMEM; the epilogue thread that owns lane j reads its 64 pre-activations, and
 // writes DP back INTO TENSOR MEMORY (hi in place of PRE, lo in a second region) with tcgen05.st,
@@ -162,7 +165,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         for (int i = 0; i < n_my && i < kRawStages; ++i) issue_raw(i);
     }
     if (warp == 18) tc::tmem_alloc(&bars->tmem_base, 512);
-    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/false);
+    tc::stage_w1_tiles(w_hi, w_lo, W1, b1, H, O, tid, kThreads, /*bias_column=*/true);
     pdl_wait();
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -176,13 +179,10 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         const int jl = 32 * q + lane, j = 128 * blk + jl;
         // Two batch rows per step in packed fp32 pairs (.x = even row, .y = odd row).
         float2 w2p[NP], gw2p[NP];
-        float2 gb1p = make_float2(0.f, 0.f);
 #pragma unroll
         for (int n = 0; n < NP; ++n) gw2p[n] = make_float2(0.f, 0.f);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
         if (blk < nblk) {
-            const float b1j = __ldg(b1 + j);
-            const float2 b1p = make_float2(b1j, b1j);
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
                 const float w = n < a.N2 ? __ldg(W2 + (size_t)n * H + j) : 0.f;
@@ -213,18 +213,15 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                     } else {
                         dz[0] = *reinterpret_cast<const float2*>(zp);
                     }
-                    const float2 pre = tc::fadd2(make_float2(v[2 * pr], v[2 * pr + 1]), b1p);
-                    // relu and relu' as one 0/1 mask (FSET) and packed multiplies; relu'(0) = 0 as
-                    // in torch
-                    const float2 m = make_float2(pre.x > 0.f ? 1.f : 0.f, pre.y > 0.f ? 1.f : 0.f);
-                    const float2 h = tc::fmul2(pre, m);
+                    // relu on the ALU pipe (FMNMX), relu' as a select (FSEL); relu'(0) = 0 as in torch
+                    const float2 pre = make_float2(v[2 * pr], v[2 * pr + 1]);
+                    const float2 h = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
                     float2 dh = tc::fmul2(dz[0], w2p[0]);
 #pragma unroll
                     for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
 #pragma unroll
                     for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
-                    const float2 dp = tc::fmul2(dh, m);
-                    gb1p = tc::fadd2(gb1p, dp);
+                    const float2 dp = make_float2(pre.x > 0.f ? dh.x : 0.f, pre.y > 0.f ? dh.y : 0.f);
                     // hi = dp truncated to tf32 (one LOP3; cvt.rna.tf32 is a 4-instruction
                     // sequence on sm_100), lo = the exact remainder < 2^-10 |dp|
                     float2 hi;
@@ -245,8 +242,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 tc::mbar_arrive(&bars->dp_full[d1]);
                 TRACE(i, 4)
             }
-            if (hh == 1) {  // hand this half's sums to the thread that owns the other half
-                exch[j] = gb1p.x + gb1p.y;
+            if (hh == 1) {  // hand this half's dW2 sums to the thread that owns the other half
 #pragma unroll
                 for (int n = 0; n < NP; ++n) exch[(n + 1) * 256 + j] = gw2p[n].x + gw2p[n].y;
             }
@@ -263,10 +259,13 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             for (int k = 0; k < 32; ++k) g[k] += g2[k];
             float* wsb = a.ws + (size_t)cta * a.lay.total;
             float4* wrow = reinterpret_cast<float4*>(wsb + a.lay.oW1 + (size_t)j * O);
+            float gb1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < 8; ++c) {
                 if (c < ochunks) wrow[c] = make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-            wsb[a.lay.ob1 + j] = (gb1p.x + gb1p.y) + exch[j];
+                else if (c == ochunks) gb1 = g[4 * c];  // column O of dW1': sum of DP over the rows = db1
+            }
+            wsb[a.lay.ob1 + j] = gb1;
 #pragma unroll
             for (int n = 0; n < NP; ++n)
                 if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * H + j] = (gw2p[n].x + gw2p[n].y) + exch[(n + 1) * 256 + j];
@@ -320,6 +319,9 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                         if (n < a.N2) z[n] = __ldg(a.dout + (size_t)row * a.N2 + n);
                 }
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c == ochunks) v[c].x = 1.f;  // column O of X': multiplies b1 (UMMA1), sums DP into db1 (UMMA2)
             asm volatile("bar.sync 1, 64;" ::: "memory");  // both producer warps drained the raw stage
             if (pw == 0 && lane == 0 && i + kRawStages < n_my) issue_raw(i + kRawStages);
             tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMA2 that read this stage has retired
@@ -381,7 +383,7 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
         const uint32_t idesc1 = tc::instr_desc_tf32_m128(kRowsT);  // N = 64 batch rows
         const uint32_t idesc2w = tc::instr_desc_tf32_m128(2 * kKPad);  // N = 64: [hi | lo] features
         const uint32_t idesc2 = tc::instr_desc_tf32_m128(kKPad);       // N = 32: hi features
-        const int ksteps1 = (O + 7) >> 3;  // K' columns in use
+        const int ksteps1 = (O + 1 + 7) >> 3;  // K' columns in use: O features + the bias column
         const uint64_t dw_hi = tc::smem_desc_k_sw128(w_hi, 0), dw_lo = tc::smem_desc_k_sw128(w_lo, 0);
         const uint64_t dx_hi = tc::smem_desc_k_sw128(x_hi, 0), dx_lo = tc::smem_desc_k_sw128(x_lo, 0);
         const uint64_t dxt = tc::smem_desc_k_sw128(xt, 0);

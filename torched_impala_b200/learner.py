@@ -430,8 +430,13 @@ class Learner:
                 leader.wait_ready()
             done, slot, pending, stage_k = 0, 0, None, 0
             B_loc = self.hp.batch_size // world
+            to_release = []  # (DMA-done event, ring slab): released one iteration later, off the critical path
             while done < self.hp.max_updates:
                 # ---- batch i: collect (host), DMA (copy stream) - the kernels of batch i-1 are running
+                while to_release:
+                    ev, kk = to_release.pop(0)
+                    ev.synchronize()
+                    ring.release(kk)
                 if ring is not None:
                     try:
                         k, reward = ring.collect_batch(self.timeout)
@@ -455,8 +460,7 @@ class Learner:
                         ring.release(k)
                 elif ring is not None:
                     eng.ingest_from(ring.slab_address(k), slot)   # DMA straight out of shared memory
-                    eng.slab_ready[slot].synchronize()
-                    ring.release(k)
+                    to_release.append((eng.slab_ready[slot], k))  # handed back to the actors once the DMA is done
                 else:
                     eng.ingest(slot)
                 eng.step(slot)

@@ -82,7 +82,7 @@ class RingQueue:
         self._c = None
         self._fence = threading.Lock()  # acquire/release = a full memory fence on every platform
         self._next = 0
-        self.ids = [[None] * B for _ in range(slabs)]  # trajectory id per (slab, column), for logs
+        self.ids = [np.full(B, -1, np.int64) for _ in range(slabs)]  # trajectory id per (slab, column), for logs; -1 = none
         c = self._control()
         c["filled"][:] = 0
         c["released"][:] = 0
@@ -223,7 +223,7 @@ class RingQueue:
             _pause(last)
         self._barrier()  # flags before the payload reads
         reward = float(c["rsum"][k].sum()) / self.B
-        self.ids[k] = [int(t) if t >= 0 else None for t in c["tid"][k]]
+        self.ids[k] = c["tid"][k].copy()  # one vector copy - a python loop over B columns costs more than the DMA
         self._next = (k + 1) % self.K
         return k, reward
 
