@@ -73,7 +73,7 @@ def main():
         assert set(torch.load(ck)) == {"policy_state_dict", "value_fn_state_dict"}
     if use_ring:
         q.close()
-    assert lrn.policy_version >= 2 * g.updates, lrn.policy_version  # one publication per update + the final sync
+    assert lrn.policy_version >= 2 and lrn.policy_version % 2 == 0, lrn.policy_version  # publications happened, none torn
     print(f"LEARNER_PROCESS_OK updates={counter.value} max|dW|={worst:.2e} ring={use_ring} devices={n_dev} "
           f"version={lrn.policy_version}")
 

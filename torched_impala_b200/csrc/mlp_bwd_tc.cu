@@ -199,44 +199,59 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                 tc::tc_fence_after();
                 TRACE(i, 1)
                 const float* dz_half = dzs + (s * kRowsT + 32 * hh) * NP;  // [row pair][n][2]
-                float v[32], lo[32];
-                tc::tmem_ld32(c_hi, v);
+                // The thread's 32 pre-activations are processed as two halves of 16 columns so that
+                // tensor-memory traffic overlaps the math: the second half is in flight while the first
+                // is consumed, and DP_hi of the first half is already on its way back while the second
+                // is computed (all 16 epilogue warps start a tile together: TMEM reads at 64 B/clk
+                // and the math would otherwise simply alternate).
+                uint32_t va[16], vb[16], la[16], lb[16];
+                auto half = [&](uint32_t (&v)[16], uint32_t (&lo)[16], const int pr0) {
 #pragma unroll
-                for (int pr = 0; pr < 16; ++pr) {
-                    const float* zp = dz_half + pr * 2 * NP;
-                    float2 dz[NP];
-                    if constexpr (NP == 4) {
-                        const float4 t0 = *reinterpret_cast<const float4*>(zp);
-                        const float4 t1 = *reinterpret_cast<const float4*>(zp + 4);
-                        dz[0] = make_float2(t0.x, t0.y), dz[1] = make_float2(t0.z, t0.w);
-                        dz[2] = make_float2(t1.x, t1.y), dz[3] = make_float2(t1.z, t1.w);
-                    } else {
-                        dz[0] = *reinterpret_cast<const float2*>(zp);
+                    for (int q2 = 0; q2 < 8; ++q2) {
+                        const int pr = pr0 + q2;
+                        const float* zp = dz_half + pr * 2 * NP;
+                        float2 dz[NP];
+                        if constexpr (NP == 4) {
+                            const float4 t0 = *reinterpret_cast<const float4*>(zp);
+                            const float4 t1 = *reinterpret_cast<const float4*>(zp + 4);
+                            dz[0] = make_float2(t0.x, t0.y), dz[1] = make_float2(t0.z, t0.w);
+                            dz[2] = make_float2(t1.x, t1.y), dz[3] = make_float2(t1.z, t1.w);
+                        } else {
+                            dz[0] = *reinterpret_cast<const float2*>(zp);
+                        }
+                        // relu on the ALU pipe (FMNMX), relu' as a select (FSEL); relu'(0) = 0 as in torch
+                        const float2 pre = make_float2(__uint_as_float(v[2 * q2]), __uint_as_float(v[2 * q2 + 1]));
+                        const float2 h = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
+                        float2 dh = tc::fmul2(dz[0], w2p[0]);
+#pragma unroll
+                        for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
+                        const float2 dp = make_float2(pre.x > 0.f ? dh.x : 0.f, pre.y > 0.f ? dh.y : 0.f);
+                        // hi = dp truncated to tf32 (one LOP3; cvt.rna.tf32 is a 4-instruction
+                        // sequence on sm_100), lo = the exact remainder < 2^-10 |dp|
+                        float2 hi;
+                        hi.x = __uint_as_float(__float_as_uint(dp.x) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(dp.y) & 0xffffe000u);
+                        const float2 l = tc::fsub2(dp, hi);
+                        v[2 * q2] = __float_as_uint(hi.x), v[2 * q2 + 1] = __float_as_uint(hi.y);
+                        lo[2 * q2] = __float_as_uint(l.x), lo[2 * q2 + 1] = __float_as_uint(l.y);
                     }
-                    // relu on the ALU pipe (FMNMX), relu' as a select (FSEL); relu'(0) = 0 as in torch
-                    const float2 pre = make_float2(v[2 * pr], v[2 * pr + 1]);
-                    const float2 h = make_float2(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f));
-                    float2 dh = tc::fmul2(dz[0], w2p[0]);
-#pragma unroll
-                    for (int n = 1; n < NP; ++n) dh = tc::ffma2(dz[n], w2p[n], dh);
-#pragma unroll
-                    for (int n = 0; n < NP; ++n) gw2p[n] = tc::ffma2(dz[n], h, gw2p[n]);
-                    const float2 dp = make_float2(pre.x > 0.f ? dh.x : 0.f, pre.y > 0.f ? dh.y : 0.f);
-                    // hi = dp truncated to tf32 (one LOP3; cvt.rna.tf32 is a 4-instruction
-                    // sequence on sm_100), lo = the exact remainder < 2^-10 |dp|
-                    float2 hi;
-                    hi.x = __uint_as_float(__float_as_uint(dp.x) & 0xffffe000u);
-                    hi.y = __uint_as_float(__float_as_uint(dp.y) & 0xffffe000u);
-                    const float2 l = tc::fsub2(dp, hi);
-                    v[2 * pr] = hi.x, v[2 * pr + 1] = hi.y;
-                    lo[2 * pr] = l.x, lo[2 * pr + 1] = l.y;
-                }
-                tc::tmem_st32(c_hi, v);  // DP_hi replaces PRE in place
+                };
+                tc::tmem_ld16_nowait(c_hi, va);
+                tc::tmem_wait_ld16(va);
+                tc::tmem_ld16_nowait(c_hi + 16, vb);  // in flight while the first half is processed
+                half(va, la, 0);
+                tc::tmem_st16(c_hi, va);              // DP_hi replaces PRE in place
+                tc::tmem_wait_ld16(vb);
+                half(vb, lb, 8);
+                tc::tmem_st16(c_hi + 16, vb);
                 TRACE(i, 2)
                 tc::mbar_wait(&bars->lo_free, (i & 1) ^ 1);  // UMMA2 of the previous tile retired
                 tc::tc_fence_after();
                 TRACE(i, 3)
-                tc::tmem_st32(c_lo, lo);
+                tc::tmem_st16(c_lo, la);
+                tc::tmem_st16(c_lo + 16, lb);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars->dp_full[d1]);

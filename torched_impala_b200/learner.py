@@ -107,7 +107,8 @@ class _Publisher:
 
     post(n): [learner stream] policy block -> device staging buffer (freezes update n's weights
     without stalling the next update), [side stream] staging -> pinned host snapshot; the
-    publisher thread waits for that copy and writes the float64 shared tensors under a seqlock."""
+    publisher thread waits for that copy and writes the float64 shared tensors under a seqlock.
+    Two snapshot slots; publications coalesce when the host cannot keep up with the updates."""
 
     def __init__(self, eng, policy, version):
         self.eng, self.policy, self.version = eng, policy, version
@@ -130,10 +131,17 @@ class _Publisher:
         self.thread = threading.Thread(target=self._run, name="impala-publisher", daemon=True)
         self.thread.start()
 
-    def post(self, n: int) -> None:
+    def post(self, n: int, force: bool = False) -> bool:
+        """Publish the weights of update n.  Coalescing: if the previous publication is still being
+        written the call returns False at once (the next one carries newer weights anyway) - the
+        actors always see the newest weights the host can deliver, the update loop never waits.
+        force=True (evaluation / checkpoint points, last update) waits for a free snapshot slot."""
         s = self.i & 1
+        if not self.free[s].is_set():
+            if not force:
+                return False
+            self.free[s].wait()
         self.i += 1
-        self.free[s].wait()          # the host copy that last used this snapshot slot has finished
         self.free[s].clear()
         eng = self.eng
         with torch.cuda.stream(eng.stream):
@@ -146,6 +154,7 @@ class _Publisher:
             landed = torch.cuda.Event()
             landed.record(self.stream)
         self.q.put((s, n, landed))
+        return True
 
     def _run(self) -> None:
         try:
@@ -465,10 +474,15 @@ class Learner:
                     eng.ingest(slot)
                 eng.step(slot)
                 n = done + 1
-                ticket = eng.post_scalars()
+                # the logged scalars: read back when somebody consumes them (TensorBoard / console), else
+                # every 64th update (keeps the data-parallel error word checked)
+                want_scalars = writer is not None or self.hp.verbose >= 1 or n % 64 == 0 or n >= self.hp.max_updates
+                ticket = eng.post_scalars() if want_scalars else None
                 due = self._due(n)  # evaluation / checkpoint of exactly update n
+                if due and ticket is None:
+                    ticket = eng.post_scalars()
                 if due or n % self.publish_every == 0 or n >= self.hp.max_updates:
-                    pub.post(n)
+                    pub.post(n, force=due or n >= self.hp.max_updates)
                 if pub.error is not None:
                     raise pub.error
                 # ---- while update n runs: log update n - 1
@@ -508,8 +522,9 @@ class Learner:
                 writer.close()
 
     def _finish_update(self, writer, eng, pub, ticket, n, reward):
-        sc = eng.fetch_scalars(ticket)
-        self._report(writer, n, reward, sc)
+        if ticket is not None:
+            sc = eng.fetch_scalars(ticket)
+            self._report(writer, n, reward, sc)
         self._periodic(writer, n, eng, pub)
 
     # ------------------------------------------------------ checkpoints (learner.py:277-295)
