@@ -682,7 +682,7 @@ int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* 
     if (grid > kMaxParts) grid = kMaxParts;
     if (grid < 2) return IMPALA_ERR_UNSUPPORTED_SHAPE;
     const int n_pi = impala_pair_split(a_pi.num_tiles, a_vf.num_tiles, grid,
-                                       impala_env_int("IMPALA_PAIR_W_BWD", 127) * (H_pi / 128),
+                                       impala_env_int("IMPALA_PAIR_W_BWD", 105) * (H_pi / 128),
                                        100 * (H_vf / 128));
     e = push ? impala_launch(mlp_bwd_tc_pair_kernel<true>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, *push, extra, n_extra)
              : impala_launch(mlp_bwd_tc_pair_kernel<false>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, PushArgs{},

@@ -160,8 +160,7 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             uint32_t raw0[32], raw1[32];
             if (ch0 < nch) tc::tmem_ld32_nowait(taddr + 32 * ch0, raw0);
             if (ch1 < nch) tc::tmem_ld32_nowait(taddr + 32 * ch1, raw1);
-            tc::tmem_wait_ld32(raw0);
-            tc::tmem_wait_ld32(raw1);
+            tc::tmem_wait_ld();
             tc::tc_fence_before();
             tc::mbar_arrive(&bars->acc_empty[as]);  // all of this thread's TMEM reads are complete
             auto second_layer = [&](const uint32_t (&raw)[32], const int c0) {

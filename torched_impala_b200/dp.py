@@ -38,10 +38,15 @@ _WORDS = 32
 _POLL_S = 2e-5
 
 
+_OWNED: set = set()  # segments created by THIS process (their tracker registration must stay)
+
+
 def attach_untracked(name: str) -> shared_memory.SharedMemory:
     """Attach to an existing segment WITHOUT registering it with this interpreter's resource tracker
     (Python < 3.13 registers on attach and would unlink the owner's segment when a worker exits)."""
     shm = shared_memory.SharedMemory(name=name)
+    if shm.name in _OWNED:
+        return shm
     try:
         from multiprocessing import resource_tracker
 
@@ -57,6 +62,7 @@ class ShardControl:
     def __init__(self, name: str | None = None):
         if name is None:
             self.shm = shared_memory.SharedMemory(create=True, size=_WORDS * 8)
+            _OWNED.add(self.shm.name)
             self.owner = True
         else:
             self.shm = attach_untracked(name)
