@@ -152,38 +152,39 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
             float2 acc[NP == 4 ? 2 : 1];
 #pragma unroll
             for (int k = 0; k < (NP == 4 ? 2 : 1); ++k) acc[k] = b2p[k];
-            // Both 32-column chunks of this thread are requested before the first one is consumed: the
-            // tensor-memory read of the second overlaps the FMA work on the first (the epilogue is bound
-            // by TMEM read bandwidth, 64 B/clk/SM), and the accumulator stage goes back to the UMMA
-            // issuer as soon as the loads have landed - before, not after, the second-layer math.
-            const int ch0 = grp, ch1 = grp + 4;
-            uint32_t raw0[32], raw1[32];
-            if (ch0 < nch) tc::tmem_ld32_nowait(taddr + 32 * ch0, raw0);
-            if (ch1 < nch) tc::tmem_ld32_nowait(taddr + 32 * ch1, raw1);
-            tc::tmem_wait_ld();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&bars->acc_empty[as]);  // all of this thread's TMEM reads are complete
-            auto second_layer = [&](const uint32_t (&raw)[32], const int c0) {
+            // chunk by chunk (32 live accumulator registers at a time: 672 threads leave 80 each)
+#pragma unroll 1
+            for (int hb = 0; hb < 2; ++hb) {
+                const int ch = grp + 4 * hb;
+                const bool last = ch + 4 >= nch || hb == 1;
+                float raw[32];
+                if (ch < nch) tc::tmem_ld32(taddr + 32 * ch, raw);  // waits for the data
+                if (last) {  // all of this thread's TMEM reads are complete: release the stage
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&bars->acc_empty[as]);
+                }
+                if (ch < nch) {
+                    const int c0 = 32 * ch;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float h0 = fmaxf(__uint_as_float(raw[i]), 0.f);
-                    const float h1 = fmaxf(__uint_as_float(raw[i + 1]), 0.f);
-                    if constexpr (NP == 4) {
-                        const float4 wa = *reinterpret_cast<const float4*>(w2s + (c0 + i) * 4);
-                        const float4 wb = *reinterpret_cast<const float4*>(w2s + (c0 + i + 1) * 4);
-                        const float2 h0p = make_float2(h0, h0), h1p = make_float2(h1, h1);
-                        acc[0] = tc::ffma2(h0p, make_float2(wa.x, wa.y), acc[0]);
-                        acc[1] = tc::ffma2(h0p, make_float2(wa.z, wa.w), acc[1]);
-                        acc[0] = tc::ffma2(h1p, make_float2(wb.x, wb.y), acc[0]);
-                        acc[1] = tc::ffma2(h1p, make_float2(wb.z, wb.w), acc[1]);
-                    } else {
-                        const float2 w = *reinterpret_cast<const float2*>(w2s + c0 + i);
-                        acc[0] = tc::ffma2(make_float2(h0, h1), w, acc[0]);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float h0 = fmaxf(raw[i], 0.f);
+                        const float h1 = fmaxf(raw[i + 1], 0.f);
+                        if constexpr (NP == 4) {
+                            const float4 wa = *reinterpret_cast<const float4*>(w2s + (c0 + i) * 4);
+                            const float4 wb = *reinterpret_cast<const float4*>(w2s + (c0 + i + 1) * 4);
+                            const float2 h0p = make_float2(h0, h0), h1p = make_float2(h1, h1);
+                            acc[0] = tc::ffma2(h0p, make_float2(wa.x, wa.y), acc[0]);
+                            acc[1] = tc::ffma2(h0p, make_float2(wa.z, wa.w), acc[1]);
+                            acc[0] = tc::ffma2(h1p, make_float2(wb.x, wb.y), acc[0]);
+                            acc[1] = tc::ffma2(h1p, make_float2(wb.z, wb.w), acc[1]);
+                        } else {
+                            const float2 w = *reinterpret_cast<const float2*>(w2s + c0 + i);
+                            acc[0] = tc::ffma2(make_float2(h0, h1), w, acc[0]);
+                        }
                     }
                 }
-            };
-            if (ch0 < nch) second_layer(raw0, 32 * ch0);
-            if (ch1 < nch) second_layer(raw1, 32 * ch1);
+                if (last) break;
+            }
             TRACE(it, 2)
             const int rl = 32 * q + lane;  // row of the tile
             float* pbuf = part + (it & 1) * 3 * kTileM * NP;
