@@ -96,19 +96,32 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
-static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                        cudaStream_t st, bool dependent, Args&&... args) {
+static inline cudaError_t impala_launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, bool dependent, bool cooperative, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     unsigned n = 0;
     if (dependent && impala_env_int("IMPALA_PDL", 0) != 0) {
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        n = 1;
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cooperative) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
     }
     cfg.attrs = attr, cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// cooperative: the kernel contains a grid-wide barrier - the launch then FAILS (instead of the barrier
+// hanging) when the CTAs cannot all be resident, e.g. under an MPS SM limit or in a green context.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t impala_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, bool dependent, Args&&... args) {
+    return impala_launch_ex(kernel, grid, block, smem, st, dependent, false, static_cast<Args&&>(args)...);
 }
 
 // ---- push-model all-reduce over peer memory, LL ("low latency") format (protocol: see optim.cu)

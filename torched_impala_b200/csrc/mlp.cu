@@ -75,13 +75,16 @@ bool pick_config(int O, int H, int N2, bool bwd, MlpConfig* c) {
     else if (N2 <= 4) c->np = 4;
     else if (N2 <= 16) c->np = 16;
     else return false;
-    // register budget: forward holds JPT*OP weights, backward 2*JPT*OP (weights + gradient)
+    // register budget: forward holds JPT*OP weights, backward 2*JPT*OP (weights + gradient); at OP = 64
+    // the backward splits the features of a hidden unit over a lane pair (ks = 2: 2 x 32 + 2 x 32)
+    c->ks = (bwd && c->op == 64) ? 2 : 1;
     if (H < 128 || (bwd && c->op == 64)) c->jpt = 1, c->maxt = bwd && H >= 128 ? 256 : 128;
     else c->jpt = 2, c->maxt = 256;
-    const int want = (int)impala_round_up((H + c->jpt - 1) / c->jpt, 32);
+    const int want = (int)impala_round_up((int64_t)c->ks * ((H + c->jpt - 1) / c->jpt), 32);
     if (bwd) {
         c->threads = want < c->maxt ? want : c->maxt;
-        c->slices = (H + c->threads * c->jpt - 1) / (c->threads * c->jpt);
+        const int units = c->threads / c->ks * c->jpt;  // hidden units per CTA
+        c->slices = (H + units - 1) / units;
     } else {
         if (want > c->maxt) return false;  // forward needs the whole hidden layer in one CTA
         c->threads = want;

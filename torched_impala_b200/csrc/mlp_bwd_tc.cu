@@ -480,8 +480,9 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
     return raw;
 }
 
-// Grid barrier: every CTA of the launch is resident (grid <= SM count, one CTA per SM).  ctl[0]
-// counts arrivals; a workspace that was not zero-filled once traps instead of hanging.
+// Grid barrier: every CTA of the launch is resident (grid <= SM count, one CTA per SM, COOPERATIVE
+// launch - it fails instead of hanging where co-residency cannot be had).  ctl[0] counts arrivals; a
+// workspace that was not zero-filled once traps instead of hanging.
 __device__ __forceinline__ void grid_arrive_and_wait(unsigned int* ctl) {
     if (threadIdx.x == 0) {
         atomicAdd(ctl, 1u);
@@ -652,7 +653,7 @@ int impala_mlp_bwd_tc(const float* x, const float* params, const float* dout, fl
     }
     int grid = a.num_tiles < sms ? a.num_tiles : sms;  // <= SM count: the grid barrier needs residency
     if (grid > kMaxParts) grid = kMaxParts;
-    if ((e = impala_launch(kernel, grid, kThreads, kSmemBytes, st, true, a)) != cudaSuccess) return (int)e;
+    if ((e = impala_launch_ex(kernel, grid, kThreads, kSmemBytes, st, true, true, a)) != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
 
@@ -684,9 +685,11 @@ int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* 
     const int n_pi = impala_pair_split(a_pi.num_tiles, a_vf.num_tiles, grid,
                                        impala_env_int("IMPALA_PAIR_W_BWD", 105) * (H_pi / 128),
                                        100 * (H_vf / 128));
-    e = push ? impala_launch(mlp_bwd_tc_pair_kernel<true>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, *push, extra, n_extra)
-             : impala_launch(mlp_bwd_tc_pair_kernel<false>, grid, kThreads, kSmemBytes, st, true, a_pi, a_vf, n_pi, PushArgs{},
-                             (const double*)nullptr, 0);
+    // cooperative launch: the in-kernel grid barrier needs every CTA resident
+    e = push ? impala_launch_ex(mlp_bwd_tc_pair_kernel<true>, grid, kThreads, kSmemBytes, st, true, true, a_pi, a_vf, n_pi, *push,
+                                extra, n_extra)
+             : impala_launch_ex(mlp_bwd_tc_pair_kernel<false>, grid, kThreads, kSmemBytes, st, true, true, a_pi, a_vf, n_pi,
+                                PushArgs{}, (const double*)nullptr, 0);
     if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }

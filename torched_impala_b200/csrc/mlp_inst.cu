@@ -24,10 +24,18 @@
         default: return impala_mlp_launch(KERNEL<JPT, IMPALA_OP, 16, MAXT>, a, c, smem, st, grid); \
     }
 
+#define BY_NP_KS2(MAXT)                                                                          \
+    switch (c.np) {                                                                              \
+        case 1: return impala_mlp_launch(KERNEL<1, IMPALA_OP, 1, MAXT, 2>, a, c, smem, st, grid);    \
+        case 4: return impala_mlp_launch(KERNEL<1, IMPALA_OP, 4, MAXT, 2>, a, c, smem, st, grid);    \
+        default: return impala_mlp_launch(KERNEL<1, IMPALA_OP, 16, MAXT, 2>, a, c, smem, st, grid);  \
+    }
+
 int ENTRY(const MlpArgs& a, const MlpConfig& c, size_t smem, cudaStream_t st, int* grid) {
 #if IMPALA_BWD && IMPALA_OP == 64
-    if (c.maxt == 128) { BY_NP(1, 128) }
-    BY_NP(1, 256)
+    // wide observations: a lane pair per hidden unit (KS = 2), see mlp_kernels.cuh
+    if (c.maxt == 128) { BY_NP_KS2(128) }
+    BY_NP_KS2(256)
 #else
     if (c.jpt == 1) { BY_NP(1, 128) }
     BY_NP(2, 256)

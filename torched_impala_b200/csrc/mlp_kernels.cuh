@@ -18,6 +18,7 @@ struct MlpArgs {
 
 struct MlpConfig {
     int jpt, maxt, op, np, threads, slices;
+    int ks;  // backward: threads per hidden unit (2 = the observation features are split over a lane pair)
 };
 
 constexpr int kRows = 32;        // rows per staged tile
@@ -215,25 +216,35 @@ __device__ __forceinline__ void zero_range(float* p, int64_t lo, int64_t hi) {
 }
 
 // grid = (persistent row-tile CTAs, hidden slices): CTA (bx, by) owns hidden units
-// [by * nt * JPT, (by+1) * nt * JPT) and writes that part of partial row bx.
-template <int JPT, int OP, int NP, int MAXT>
+// [by * (nt / KS) * JPT, (by+1) * (nt / KS) * JPT) and writes that part of partial row bx.
+// KS = 2 (wide observations, OP = 64): a hidden unit is shared by a lane pair, each lane keeps HALF of
+// its W1 row and of its dW1 row in registers (2 x 32 instead of 2 x 64 - the one-thread-per-unit
+// form spilled ~1.5 KB per thread at this width); the two partial dot products of the recompute
+// meet through one shuffle per row, everything downstream of the pre-activation is computed by
+// both lanes and stored by the even one.
+template <int JPT, int OP, int NP, int MAXT, int KS = 1>
 __global__ void __launch_bounds__(MAXT) mlp_bwd_kernel(MlpArgs a) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int OPH = OP / KS;  // features held by this thread
     const int nt = blockDim.x, tid = threadIdx.x;
-    const int j0 = blockIdx.y * nt * JPT + tid;
+    const int half = KS == 2 ? (tid & 1) : 0, ju = KS == 2 ? (tid >> 1) : tid, nu = nt / KS;
+    const int j0 = blockIdx.y * nu * JPT + ju;
+    const int koff = half * OPH;
     float* xs = smem;               // [kRows][OP]
     float* dzs = xs + kRows * OP;   // [kRows][NP]
     const float* __restrict__ W1 = a.params + a.lay.oW1;
     const float* __restrict__ b1 = a.params + a.lay.ob1;
     const float* __restrict__ W2 = a.params + a.lay.oW2;
 
-    float w[JPT][OP], b1r[JPT], w2r[JPT][NP];
-    float gw1[JPT][OP], gb1[JPT], gw2[JPT][NP], gb2 = 0.f;
-    load_w1<JPT, OP>(w, W1, j0, nt, a.H, a.O);
+    float w[JPT][OPH], b1r[JPT], w2r[JPT][NP];
+    float gw1[JPT][OPH], gb1[JPT], gw2[JPT][NP], gb2 = 0.f;
 #pragma unroll
     for (int q = 0; q < JPT; ++q) {
-        const int j = j0 + q * nt;
-        b1r[q] = j < a.H ? __ldg(b1 + j) : 0.f;
+        const int j = j0 + q * nu;
+#pragma unroll
+        for (int k = 0; k < OPH; ++k)
+            w[q][k] = (j < a.H && koff + k < a.O) ? __ldg(W1 + (size_t)j * a.O + koff + k) : 0.f;
+        b1r[q] = (j < a.H && half == 0) ? __ldg(b1 + j) : 0.f;  // added once per unit
         gb1[q] = 0.f;
 #pragma unroll
         for (int n = 0; n < NP; ++n) {
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(MAXT) mlp_bwd_kernel(MlpArgs a) {
             gw2[q][n] = 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < OP; ++k) gw1[q][k] = 0.f;
+        for (int k = 0; k < OPH; ++k) gw1[q][k] = 0.f;
     }
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -256,10 +267,34 @@ __global__ void __launch_bounds__(MAXT) mlp_bwd_kernel(MlpArgs a) {
         __syncthreads();
 #pragma unroll 1
         for (int g = 0; g < kRows / kGroup; ++g) {
-            const float* xg = xs + g * kGroup * OP;
+            const float* xg = xs + g * kGroup * OP + koff;
             const float* dzg = dzs + g * kGroup * NP;
             float acc[JPT][kGroup];
-            layer1<JPT, OP>(acc, w, xg, b1r);  // recompute pre-activations
+            // recompute pre-activations (this thread's features; row stride of the tile stays OP)
+#pragma unroll
+            for (int q = 0; q < JPT; ++q)
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) acc[q][r] = b1r[q];
+#pragma unroll
+            for (int k4 = 0; k4 < OPH / 4; ++k4) {
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xg + r * OP + 4 * k4);
+#pragma unroll
+                    for (int q = 0; q < JPT; ++q) {
+                        acc[q][r] = fmaf(w[q][4 * k4 + 0], xv.x, acc[q][r]);
+                        acc[q][r] = fmaf(w[q][4 * k4 + 1], xv.y, acc[q][r]);
+                        acc[q][r] = fmaf(w[q][4 * k4 + 2], xv.z, acc[q][r]);
+                        acc[q][r] = fmaf(w[q][4 * k4 + 3], xv.w, acc[q][r]);
+                    }
+                }
+            }
+            if constexpr (KS == 2) {
+#pragma unroll
+                for (int q = 0; q < JPT; ++q)
+#pragma unroll
+                    for (int r = 0; r < kGroup; ++r) acc[q][r] += __shfl_xor_sync(IMPALA_FULL_MASK, acc[q][r], 1);
+            }
 #pragma unroll
             for (int r = 0; r < kGroup; ++r) {
                 float dz[NP];
@@ -289,7 +324,7 @@ __global__ void __launch_bounds__(MAXT) mlp_bwd_kernel(MlpArgs a) {
                 }
             }
 #pragma unroll
-            for (int k4 = 0; k4 < OP / 4; ++k4) {
+            for (int k4 = 0; k4 < OPH / 4; ++k4) {
 #pragma unroll
                 for (int r = 0; r < kGroup; ++r) {
                     const float4 xv = *reinterpret_cast<const float4*>(xg + r * OP + 4 * k4);
@@ -312,15 +347,17 @@ __global__ void __launch_bounds__(MAXT) mlp_bwd_kernel(MlpArgs a) {
     float* wsb = a.ws + (size_t)blockIdx.x * a.lay.total;
 #pragma unroll
     for (int q = 0; q < JPT; ++q) {
-        const int j = j0 + q * nt;
+        const int j = j0 + q * nu;
         if (j < a.H) {
 #pragma unroll
-            for (int k = 0; k < OP; ++k)
-                if (k < a.O) wsb[a.lay.oW1 + (size_t)j * a.O + k] = gw1[q][k];
-            wsb[a.lay.ob1 + j] = gb1[q];
+            for (int k = 0; k < OPH; ++k)
+                if (koff + k < a.O) wsb[a.lay.oW1 + (size_t)j * a.O + koff + k] = gw1[q][k];
+            if (half == 0) {
+                wsb[a.lay.ob1 + j] = gb1[q];
 #pragma unroll
-            for (int n = 0; n < NP; ++n)
-                if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * a.H + j] = gw2[q][n];
+                for (int n = 0; n < NP; ++n)
+                    if (n < a.N2) wsb[a.lay.oW2 + (size_t)n * a.H + j] = gw2[q][n];
+            }
         }
     }
     if (blockIdx.y == 0) {

@@ -438,7 +438,6 @@ class Learner:
             if leader is not None:
                 leader.wait_ready()
             done, slot, pending, stage_k = 0, 0, None, 0
-            B_loc = self.hp.batch_size // world
             to_release = []  # (DMA-done event, ring slab): released one iteration later, off the critical path
             while done < self.hp.max_updates:
                 # ---- batch i: collect (host), DMA (copy stream) - the kernels of batch i-1 are running
