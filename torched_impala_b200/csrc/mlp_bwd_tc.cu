@@ -536,20 +536,28 @@ __device__ __forceinline__ void reduce_rows(const BwdTcArgs& a, const int nparts
         s_red[warp * 64 + 2 * lane] = sx;
         s_red[warp * 64 + 2 * lane + 1] = sy;
         __syncthreads();
-        if (warp == 0 && e0 < total) {
+        if (push) {
+            // Warp r sends the chunk to rank r: lane l carries entries l and l + 32, so each store
+            // instruction covers 512 contiguous bytes of the peer's slot (4 full 128-byte lines).
+            // Remote stores are credit-limited per SM - with 16-byte scattered requests from a single
+            // warp this tail cost 12 us at 8 GPUs.  Same summation order as below: every rank (and
+            // the single-GPU path) forms bit-identical values.
+            if (warp < push->world) {
+                const int64_t ea = (int64_t)c * 64 + lane, eb = ea + 32;
+                double va = 0.0, vb = 0.0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) va += s_red[w * 64 + lane], vb += s_red[w * 64 + 32 + lane];
+                const long long step = *push->seq + 1;
+                ulonglong2* dst = push->gather[warp] + (step & 1) * push->buf_stride +
+                                  (int64_t)push->rank * push->slot_stride + push_off;
+                if (ea < total) ll_store(dst + ea, va, (unsigned)step);
+                if (eb < total) ll_store(dst + eb, vb, (unsigned)step);
+            }
+        } else if (warp == 0 && e0 < total) {
             double tx = 0.0, ty = 0.0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) tx += s_red[w * 64 + 2 * lane], ty += s_red[w * 64 + 2 * lane + 1];
-            if (push) {  // LL stores (common.cuh): value + step tag, no fence, no flag
-                const long long step = *push->seq + 1;
-                const int64_t off = (step & 1) * push->buf_stride + (int64_t)push->rank * push->slot_stride + push_off + e0;
-                for (int r = 0; r < push->world; ++r) {
-                    ll_store(push->gather[r] + off, tx, (unsigned)step);
-                    ll_store(push->gather[r] + off + 1, ty, (unsigned)step);
-                }
-            } else {
-                *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
-            }
+            *reinterpret_cast<double2*>(a.grad + e0) = make_double2(tx, ty);
         }
         __syncthreads();
     }

@@ -153,7 +153,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-constexpr int kPushCtas = 16, kPushThreads = 256;
+constexpr int kPushThreads = 256;  // remote stores are credit-limited per SM: spread the message over many CTAs
 
 // Stand-alone producer: local[0, n) -> slot `rank` of every rank's gather buffer.
 __global__ void __launch_bounds__(kPushThreads)
@@ -335,7 +335,12 @@ extern "C" int impala_peer_push(const double* local, int64_t n, void* const* pee
     if (n < 1 || world < 1 || world > 8 || rank < 0 || rank >= world) return IMPALA_ERR_BAD_ARG;
     if (slot_stride < n || buf_stride < (int64_t)world * slot_stride) return IMPALA_ERR_BAD_ARG;
     PushArgs p{reinterpret_cast<ulonglong2* const*>(peer_gather), seq, slot_stride, buf_stride, rank, world};
-    const cudaError_t e = impala_launch(peer_push_kernel, kPushCtas, kPushThreads, 0, (cudaStream_t)stream, true, local, n, p);
+    int sms = 0;
+    cudaError_t e = impala_sm_count(&sms);
+    if (e != cudaSuccess) return (int)e;
+    int grid = (int)((n + kPushThreads - 1) / kPushThreads);
+    if (grid > sms) grid = sms;
+    e = impala_launch(peer_push_kernel, grid, kPushThreads, 0, (cudaStream_t)stream, true, local, n, p);
     if (e != cudaSuccess) return (int)e;
     return impala_launch_status();
 }
