@@ -47,11 +47,12 @@ def main():
                  ws=torch.zeros(int(lib.impala_vtrace_loss_workspace(T, B, A)), dtype=torch.uint8, device="cuda"))
         by_in = 4 * T * B * (2 * A + 2) + T * B + 4 * (T + 1) * B
         by = by_in + 4 * (T + 1) * B + 4 * T * B + (4 * T * B * A + 4 * (T + 1) * B if loss else 0)
-        for S in (1, 2, 5):
-            for nseg in ({1: (8, 16, 20, 32), 2: (4, 8, 10, 16), 5: (4, 5, 8, 10)}[S]):
-                if S * nseg < min(T, 10) or (S == 1 and T > 32 and nseg != 32):
-                    continue
+        combos = [(2, 8, 1), (2, 13, 4), (2, 7, 8), (2, 4, 8), (2, 16, 4), (5, 5, 4), (5, 4, 8)] if T > 32 else \
+                 [(2, 10, 1), (1, 20, 1), (2, 5, 2), (2, 3, 4)]
+        for S, nseg, cl in combos:
+            if True:
                 os.environ["IMPALA_VTRACE_S"], os.environ["IMPALA_VTRACE_NSEG"] = str(S), str(nseg)
+                os.environ["IMPALA_VTRACE_CLUSTER"] = str(cl)
                 P = lambda t: C.c_void_p(t.data_ptr())
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 if loss:
@@ -64,8 +65,8 @@ def main():
                         P(x["cur"]), P(x["beh"]), P(x["act"]), P(x["rew"]), P(x["don"]), P(x["lens"]), P(x["v"]), P(o["vs"]),
                         P(o["pg"]), T, B, A, 0.99, 1.0, 1.0, 0, st), "vtrace")
                 us = time_it(fn)
-                print(f"T={T} B={B} loss={int(loss)} S={S} NSEG={nseg}: {us:7.2f} us  {by / us / 1e3:7.1f} GB/s", flush=True)
-    os.environ.pop("IMPALA_VTRACE_S"), os.environ.pop("IMPALA_VTRACE_NSEG")
+                print(f"T={T} B={B} loss={int(loss)} S={S} warps/CTA={nseg} cluster={cl}: {us:7.2f} us  {by / us / 1e3:7.1f} GB/s", flush=True)
+    os.environ.pop("IMPALA_VTRACE_S"), os.environ.pop("IMPALA_VTRACE_NSEG"), os.environ.pop("IMPALA_VTRACE_CLUSTER")
 
 
 if __name__ == "__main__":

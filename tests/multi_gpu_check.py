@@ -64,7 +64,7 @@ def main():
                 assert abs(scal[u][k] - want[k]) < 1e-5 * max(1.0, abs(want[k])), (u, k, scal[u][k], want[k])
         d = (mine - ref.params).abs().max().item()
         assert d < 2e-5, d
-        print(f"MULTI_GPU_OK world={world} allreduce={'peer' if eng.peer else 'nccl'} max|dparam|={d:.2e} "
+        print(f"MULTI_GPU_OK world={world} allreduce={('peer(fused)' if eng.peer['fused'] else 'peer(standalone)') if eng.peer else 'nccl'} max|dparam|={d:.2e} "
               f"loss={scal[-1]['total_loss']:.6f} oracle: max|dvs|={par['max_abs_vs']:.1e} max|dscalar|={par['max_abs_scalar']:.1e} "
               f"rel|dgrad|={par['max_rel_grad']:.1e}")
     dist.barrier()

@@ -1,5 +1,6 @@
-"""GPU (>= 2 devices): the data-parallel learner equals the single-GPU full-batch learner, with the
-gradient all-reduce done by the optimizer kernel over NVLink peer memory (default) and by NCCL."""
+"""GPU (>= 2 devices): the data-parallel learner equals the single-GPU full-batch learner and the
+float64 oracle, with the gradient exchange as a push over NVLink peer memory from the backward's
+tail (default), from the stand-alone producer kernel, and through NCCL."""
 import os
 import socket
 import subprocess
@@ -11,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("allreduce", ["peer", "nccl"])
+@pytest.mark.parametrize("allreduce", ["peer", "peer-standalone", "nccl"])
 def test_two_rank_learner_matches_single_gpu(allreduce):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
@@ -22,10 +23,12 @@ def test_two_rank_learner_matches_single_gpu(allreduce):
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), script],
                          capture_output=True, text=True, timeout=240,
-                         env=dict(os.environ, IMPALA_ALLREDUCE=allreduce))
+                         env=dict(os.environ, IMPALA_ALLREDUCE=allreduce.split("-")[0],
+                                  IMPALA_PUSH_FUSED="0" if allreduce == "peer-standalone" else "1"))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout
-    assert f"allreduce={allreduce}" in res.stdout  # the requested path is the one that ran
+    want = {"peer": "allreduce=peer(fused)", "peer-standalone": "allreduce=peer(standalone)", "nccl": "allreduce=nccl"}[allreduce]
+    assert want in res.stdout  # the requested path is the one that ran
 
 
 @pytest.mark.parametrize("transport", ["queue", "ring"])

@@ -95,13 +95,26 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
 // (IMPALA_PDL=1 enables it; the waits are no-ops on plain launches).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// cluster_x > 1: launch as thread-block clusters of that many CTAs along x (grid.x a multiple of it).
 template <typename... KArgs, typename... Args>
 static inline cudaError_t impala_launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                            cudaStream_t st, bool dependent, bool cooperative, Args&&... args) {
+    return impala_launch_cl(kernel, grid, block, smem, st, dependent, cooperative, 1, static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t impala_launch_cl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, bool dependent, bool cooperative, int cluster_x,
+                                           Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     unsigned n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
     if (dependent && impala_env_int("IMPALA_PDL", 0) != 0) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
