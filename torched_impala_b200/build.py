@@ -37,6 +37,7 @@ def _units():
     units = [("mlp", "mlp.cu", []), ("vtrace_loss", "vtrace_loss.cu", []),
              ("optim", "optim.cu", []), ("abi", "abi.cu", []),
              ("mlp_fwd_tc", "mlp_fwd_tc.cu", []), ("mlp_bwd_tc", "mlp_bwd_tc.cu", []),
+             ("mlp_tcw", "mlp_tcw.cu", []),
              ("loss_terms", "loss_terms.cu", [])]
     for op in MLP_WIDTHS:
         for bwd in (0, 1):

@@ -156,6 +156,8 @@ extern "C" int impala_mlp_forward(const float* x, const float* params, float* ou
     const char* tc_env = std::getenv("IMPALA_MLP_TC");
     if (!(tc_env && tc_env[0] == '0') && impala_mlp_fwd_tc_eligible(x, M, O, H, N2))
         return impala_mlp_fwd_tc(x, params, out, M, O, H, N2, (cudaStream_t)stream);
+    if (!(tc_env && tc_env[0] == '0') && impala_mlp_tcw_eligible(x, M, O, H, N2))
+        return impala_mlp_fwd_tcw(x, params, out, M, O, H, N2, (cudaStream_t)stream);
     MlpArgs a{};
     MlpConfig c{};
     size_t smem;
@@ -211,7 +213,9 @@ extern "C" int impala_mlp_backward(const float* x, const float* params, const fl
         (reinterpret_cast<uintptr_t>(grad) & 15) == 0)
         return impala_mlp_bwd_tc(x, params, dout, a.ws, grad, static_cast<unsigned int*>(workspace), M, O, H,
                                  N2, (cudaStream_t)stream);  // reduces in-kernel
-    const int rc = dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
+    const bool wide = !(tc_env && tc_env[0] == '0') && impala_mlp_tcw_eligible(x, M, O, H, N2);
+    const int rc = wide ? impala_mlp_bwd_tcw(x, params, dout, a.ws, M, O, H, N2, (cudaStream_t)stream, &grid)
+                        : dispatch(true, a, c, smem, (cudaStream_t)stream, &grid);
     if (rc != IMPALA_OK) return rc;
     const int64_t total = a.lay.total;
     reduce_partials_kernel<<<(unsigned)((total + 31) / 32), kRedWarps * 32, 0,

@@ -51,6 +51,15 @@ int impala_mlp_bwd_tc_pair(const float* x, const float* params_pi, const float* 
                            int H_pi, int H_vf, int A, cudaStream_t st, const PushArgs* push = nullptr,
                            const double* extra = nullptr, int n_extra = 0);
 
+// Wide tensor-core kernels (mlp_tcw.cu): O <= 64, H a multiple of 128 (BASELINE c5: O = 64, H = 512).  The
+// forward needs no workspace; the backward leaves *nparts float32 partial rows in ws for
+// reduce_partials_kernel.  IMPALA_MLP_TCW=0 disables them.
+bool impala_mlp_tcw_eligible(const float* x, int M, int O, int H, int N2);
+int impala_mlp_fwd_tcw(const float* x, const float* params, float* out, int M, int O, int H, int N2,
+                       cudaStream_t st);
+int impala_mlp_bwd_tcw(const float* x, const float* params, const float* dout, float* ws, int M, int O, int H,
+                       int N2, cudaStream_t st, int* nparts);
+
 // One per padded observation width / direction, defined in mlp_inst.cu.
 #define IMPALA_DECL_DISPATCH(OPV)                                                             \
     int impala_mlp_fwd_op##OPV(const MlpArgs&, const MlpConfig&, size_t, cudaStream_t, int*); \

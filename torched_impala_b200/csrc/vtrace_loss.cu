@@ -386,8 +386,10 @@ constexpr int kMaxCluster = 8;  // portable cluster size
 
 // Steps per thread (S), warps per CTA (nw) and CTAs per cluster (cl); wide action sets trade S for
 // registers.  Measured on B200 (scripts/tune_vtrace.py, ncu): S = 2; up to 10 segments (T <= 20) one CTA
-// holds the whole unroll in one chunk; longer unrolls spread ceil(T / S) segments over a cluster of 8
-// CTAs (T = 100: 8 x 7 warps, one chunk), beyond 8 x 16 x S steps the chunk loop takes over.
+// holds the whole unroll in one chunk; longer unrolls walk chunks of 8 x S steps with 8 warps per CTA
+// (T = 100, B = 8192: 17.4 us).  Spreading the segments of a long unroll over a thread-block cluster
+// (DSMEM carry exchange, cl = 4 / 8) works but measured SLOWER - 34-42 us at T = 100, B = 8192: the
+// cluster barriers cost more than the chunk loop they replace - so cl = 1 unless overridden.
 // IMPALA_VTRACE_S / IMPALA_VTRACE_NSEG (warps per CTA) / IMPALA_VTRACE_CLUSTER override the choice.
 template <bool WITH_LOSS>
 int launch(VtArgs& a, cudaStream_t st) {
@@ -405,8 +407,9 @@ int launch(VtArgs& a, cudaStream_t st) {
     const int max_w = S == 5 ? 10 : (AP <= 4 && S == 1 ? kMaxSeg : 16);
     const int nseg = (a.T + S - 1) / S;
     const int cl_env = impala_env_int("IMPALA_VTRACE_CLUSTER", 0);
-    const int cl = (cl_env >= 1 && cl_env <= kMaxCluster) ? cl_env : (nseg > 10 ? kMaxCluster : 1);
+    const int cl = (cl_env >= 1 && cl_env <= kMaxCluster) ? cl_env : 1;
     int nw = (nseg + cl - 1) / cl;
+    if (cl == 1 && nw > 10) nw = 8;  // chunk loop: 8 warps per CTA measured best for long unrolls
     if (nw > max_w) nw = max_w;
     const int n_env = impala_env_int("IMPALA_VTRACE_NSEG", 0);
     if (n_env >= 1 && n_env <= max_w) nw = n_env;
