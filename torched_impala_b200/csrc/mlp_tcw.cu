@@ -66,6 +66,25 @@ __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) 
     tc::split_tf32(v.z, hi.z, lo.z);
     tc::split_tf32(v.w, hi.w, lo.w);
 }
+// The same split for the streamed operand in 3 instead of 5 SASS instructions per element (the
+// producers share issue slots with the epilogue): hi = x rounded to tf32, half away from zero (add half
+// a tf32 ulp to the magnitude bits, clear the low 13), lo = x - hi exactly.
+__device__ __forceinline__ void split_fast(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
+__device__ __forceinline__ void split4_fast(const float4& v, float4& hi, float4& lo) {
+    split_fast(v.x, hi.x, lo.x);
+    split_fast(v.y, hi.y, lo.y);
+    split_fast(v.z, hi.z, lo.z);
+    split_fast(v.w, hi.w, lo.w);
+}
+// `bytes` contiguous bytes (multiple of 16, 16-byte aligned) towards L2, no destination: issued by one
+// thread a few tiles ahead, so that the producers' register loads are L2 hits (x is re-read once per
+// hidden block and does not stay in L2 between passes: 212 MB at c5)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // Rows [128 hb, 128 hb + 128) of W1 (H, O) -> hi / lo K-major SWIZZLE_128B tiles (columns >= O zero).
 __device__ __forceinline__ void stage_w_block(uint8_t* wt, const float* __restrict__ W1, int hb, int O, int tid,
@@ -171,6 +190,33 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
             const uint32_t taddr0 = bars->tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c0;
             for (int i = 0; i < n_my; ++i, ++it) {
                 const int as = it & 1, aph = (it >> 1) & 1;
+                // the sum of the previous passes for this row - written by this very thread (plain loads,
+                // program order) - requested before the wait so that its latency is off the tile's chain
+                const int row = (cta + i * ncta) * kFTileM + rl;
+                float prev[NP];
+                if (grp == 0 && row < a.M) {
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) prev[n] = 0.f;
+                    if (hb == 0) {
+#pragma unroll
+                        for (int n = 0; n < NP; ++n)
+                            if (n < a.N2) prev[n] = __ldg(b2 + n);
+                    } else {
+                        bool vec = false;
+                        if constexpr (NP == 4) {
+                            if (a.N2 == 4) {
+                                const float4 t = *reinterpret_cast<const float4*>(a.out + (size_t)row * 4);
+                                prev[0] = t.x, prev[1] = t.y, prev[2] = t.z, prev[3] = t.w;
+                                vec = true;
+                            }
+                        }
+                        if (!vec) {
+#pragma unroll
+                            for (int n = 0; n < NP; ++n)
+                                if (n < a.N2) prev[n] = a.out[(size_t)row * a.N2 + n];
+                        }
+                    }
+                }
                 tc::mbar_wait(&bars->acc_full[as], aph);
                 tc::tc_fence_after();
                 float raw[32];
@@ -205,9 +251,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
                     else pb[0] = acc[0].x + acc[0].y;
                 }
                 asm volatile("bar.sync 2, 512;" ::: "memory");  // the four column groups meet
-                const int row = (cta + i * ncta) * kFTileM + rl;
                 if (grp == 0 && row < a.M) {
-                    // the sum of the previous passes was written by this very thread (plain loads, program order)
                     if constexpr (NP == 4) {
                         const float4 p1 = *reinterpret_cast<const float4*>(pbuf + (0 * kFTileM + rl) * 4);
                         const float4 p2 = *reinterpret_cast<const float4*>(pbuf + (1 * kFTileM + rl) * 4);
@@ -215,23 +259,16 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
                         const float z[4] = {((acc[0].x + p1.x) + p2.x) + p3.x, ((acc[0].y + p1.y) + p2.y) + p3.y,
                                             ((acc[1].x + p1.z) + p2.z) + p3.z, ((acc[1].y + p1.w) + p2.w) + p3.w};
                         if (a.N2 == 4) {
-                            float4* o4 = reinterpret_cast<float4*>(a.out + (size_t)row * 4);
-                            float4 prev;
-                            if (hb == 0) prev = make_float4(__ldg(b2), __ldg(b2 + 1), __ldg(b2 + 2), __ldg(b2 + 3));
-                            else prev = *o4;
-                            *o4 = make_float4(prev.x + z[0], prev.y + z[1], prev.z + z[2], prev.w + z[3]);
+                            *reinterpret_cast<float4*>(a.out + (size_t)row * 4) =
+                                make_float4(prev[0] + z[0], prev[1] + z[1], prev[2] + z[2], prev[3] + z[3]);
                         } else {
 #pragma unroll
                             for (int n = 0; n < 4; ++n)
-                                if (n < a.N2) {
-                                    float* o = a.out + (size_t)row * a.N2 + n;
-                                    *o = (hb == 0 ? __ldg(b2 + n) : *o) + z[n];
-                                }
+                                if (n < a.N2) a.out[(size_t)row * a.N2 + n] = prev[n] + z[n];
                         }
                     } else {
                         const float z = (((acc[0].x + acc[0].y) + pbuf[rl]) + pbuf[kFTileM + rl]) + pbuf[2 * kFTileM + rl];
-                        float* o = a.out + row;
-                        *o = (hb == 0 ? __ldg(b2) : *o) + z;
+                        a.out[row] = prev[0] + z;
                     }
                 }
             }
@@ -256,9 +293,16 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
         int it = 0;
         for (int hb = 0; hb < nblk; ++hb) {
             begin_pass(hb);
+            auto prefetch = [&](int i) {  // one thread: the tile's rows are contiguous
+                const int64_t row0 = (int64_t)(cta + i * ncta) * kFTileM;
+                const int64_t rows = a.M - row0 < kFTileM ? a.M - row0 : kFTileM;
+                if (i < n_my && rows > 0) prefetch_l2(a.x + row0 * a.O, (uint32_t)(rows * a.O * 4));
+            };
+            if (ptid == 0) prefetch(1), prefetch(2);
             if (n_my > 0) load(0);
             for (int i = 0; i < n_my; ++i, ++it) {
                 const int s = it % kFStages, ph = (it / kFStages) & 1;
+                if (ptid == 0) prefetch(i + 3);
                 tc::mbar_wait(&bars->empty[s], ph ^ 1);  // UMMAs that read this stage have retired
                 uint8_t* th = xs + s * kFStageBytes;
                 uint8_t* tl = th + 2 * kFAtomBytes;
@@ -266,7 +310,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
                 for (int k = 0; k < 8; ++k) {
                     const int idx = ptid + 256 * k, r = idx >> 4, c = idx & 15;
                     float4 hi, lo;
-                    split4(v[k], hi, lo);
+                    split4_fast(v[k], hi, lo);
                     const uint32_t off = (c >> 3) * kFAtomBytes + tc::sw128_offset(r, c & 7);
                     *reinterpret_cast<float4*>(th + off) = hi;
                     *reinterpret_cast<float4*>(tl + off) = lo;
@@ -530,11 +574,11 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
     } else if (warp < kBIssuer) {
         // ============ producer: thread = (row of the tile, K atom); 4 warps ============
         const int pw = warp - kBEpiWarps, r = 32 * (pw & 1) + lane, atom = pw >> 1, ochunks = a.O >> 2;
-        float4 v[8];
-        float z[NP];
         uint32_t xk[8];  // 16-byte chunk (lane >> 2) of a transposed row, swizzled by the row's phase k
 #pragma unroll
         for (int k = 0; k < 8; ++k) xk[k] = (static_cast<uint32_t>(lane >> 2) ^ k) << 4;
+        float4 v[8];
+        float z[NP], zn[NP];
         auto load = [&](int i) {
             const int row = (cta + i * ncta) * kBRows + r;
 #pragma unroll
@@ -544,8 +588,18 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             }
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
-                z[n] = 0.f;
-                if (atom == 0 && row < a.M && n < a.N2) z[n] = ldg_f(a.dout + (size_t)row * a.N2 + n);
+                zn[n] = 0.f;
+                if (atom == 0 && row < a.M && n < a.N2) zn[n] = ldg_f(a.dout + (size_t)row * a.N2 + n);
+            }
+        };
+        auto prefetch = [&](int i) {  // one thread: the tile's x rows (and dout rows) are contiguous
+            const int64_t row0 = (int64_t)(cta + i * ncta) * kBRows;
+            const int64_t rows = a.M - row0 < kBRows ? a.M - row0 : kBRows;
+            if (i < n_my && rows > 0) {
+                prefetch_l2(a.x + row0 * a.O, (uint32_t)(rows * a.O * 4));
+                const float* z0 = a.dout + row0 * a.N2;
+                const int64_t zb4 = rows * a.N2 * 4;
+                if ((reinterpret_cast<uintptr_t>(z0) & 15) == 0 && (zb4 & 15) == 0) prefetch_l2(z0, (uint32_t)zb4);
             }
         };
         int it = 0;
@@ -554,9 +608,11 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             float gb2[NP];
 #pragma unroll
             for (int n = 0; n < NP; ++n) gb2[n] = 0.f;
-            if (n_my > 0) load(0);
+            if (pw == 0 && lane == 0) prefetch(1), prefetch(2);
+            load(0);
             for (int i = 0; i < n_my; ++i, ++it) {
                 const int s = it & 1, ph = (it >> 1) & 1;
+                if (pw == 0 && lane == 0) prefetch(i + 3);
                 // row-major tile (B of UMMA1): free once UMMA1 of the tile two back has retired
                 tc::mbar_wait(&bars->xa_empty[s], ph ^ 1);
                 uint8_t* th = xa + s * kBXaBytes + atom * kBXAtomBytes;
@@ -564,27 +620,30 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 hi, lo;
-                    split4(v[c], hi, lo);
+                    split4_fast(v[c], hi, lo);
                     const uint32_t off = tc::sw128_offset(r, c);
                     *reinterpret_cast<float4*>(th + off) = hi;
                     *reinterpret_cast<float4*>(tl + off) = lo;
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&bars->xa_full[s]);
+#pragma unroll
+                for (int n = 0; n < NP; ++n) z[n] = zn[n];
+                // the registers are free again: the next tile's rows travel while this thread waits for
+                // the transposed stage and fills it FROM THE ROW-MAJOR TILE it has just written (its own
+                // row; the stage is not rewritten before this thread does so two tiles later)
+                if (i + 1 < n_my) load(i + 1);
                 // transposed tile (B of UMMA2: row = feature, +64 for lo; K = this warp's 32 batch rows)
                 // and dz: free once UMMA2 of the tile two back has retired
                 tc::mbar_wait(&bars->xt_empty[s], ph ^ 1);
-                // (opaque to the compiler: the split is recomputed from here on instead of 64 hi / lo values
-                // being kept - spilled - across the wait)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) asm volatile("" : "+f"(v[c].x), "+f"(v[c].y), "+f"(v[c].z), "+f"(v[c].w));
                 // feature f = 32 atom + 4 c + e -> row f of the chunk: (f >> 3) * 1024 + k * 128 + xk[k] with
                 // k = f & 7 = 4 (c & 1) + e known at compile time: eight swizzle terms, constant offsets
                 uint8_t* tth = xtb + s * kBXtBytes + (pw & 1) * kBXtChunkBytes + (lane & 3) * 4 + atom * 4096;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 hi, lo;
-                    split4(v[c], hi, lo);
+                    const uint32_t off = tc::sw128_offset(r, c);
+                    const float4 hi = *reinterpret_cast<const float4*>(th + off);
+                    const float4 lo = *reinterpret_cast<const float4*>(tl + off);
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -603,7 +662,6 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&bars->xt_full[s]);
-                if (i + 1 < n_my) load(i + 1);  // in flight while this thread waits for the next stage
             }
             if (hb == 0) {  // db2 = column sums of dout over this CTA's rows: fixed-order tree over 64 threads
 #pragma unroll
