@@ -268,8 +268,8 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
             tc::mbar_wait(&bars->done, 0);
             tc::tc_fence_after();
             float g[32], g2[32];
-            tc::tmem_ld32(lane_addr + kColAcc + blk * 64, g);        // dp_hi*x_hi + dp_lo*x_hi
-            tc::tmem_ld32(lane_addr + kColAcc + blk * 64 + 32, g2);  // dp_hi*x_lo
+            tc::tmem_ld32(lane_addr + kColAcc + blk * 64, g);        // dp_hi*x_hi
+            tc::tmem_ld32(lane_addr + kColAcc + blk * 64 + 32, g2);  // dp_hi*x_lo + dp_lo*x_hi
 #pragma unroll
             for (int k = 0; k < 32; ++k) g[k] += g2[k];
             float* wsb = a.ws + (size_t)cta * a.lay.total;
@@ -418,15 +418,18 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     if (b < nblk) {
+                        // correction terms first, hi*hi last: the accumulator addition truncates (mlp_fwd_tc.cu)
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             if (kk < ksteps1) {
                                 const uint64_t ko = 2 * kk, bo = b * kBlkOff;
-                                tc::umma_tf32(d0 + b * 64, dw_hi + bo + ko, xh + ko, idesc1, kk > 0);
-                                tc::umma_tf32(d0 + b * 64, dw_lo + bo + ko, xh + ko, idesc1, true);
+                                tc::umma_tf32(d0 + b * 64, dw_lo + bo + ko, xh + ko, idesc1, kk > 0);
                                 tc::umma_tf32(d0 + b * 64, dw_hi + bo + ko, xl + ko, idesc1, true);
                             }
                         }
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk < ksteps1) tc::umma_tf32(d0 + b * 64, dw_hi + b * kBlkOff + 2 * kk, xh + 2 * kk, idesc1, true);
                     }
                 }
                 tc::umma_commit(&bars->d1_full[d1]);
@@ -453,8 +456,9 @@ __device__ __forceinline__ uint8_t* bwd_tc_body(const BwdTcArgs& a, const int ct
                             // x^T: K-chunk kk/4 of this stage (8 KiB each), 32 bytes per step inside it
                             constexpr int kChunk16 = kXTileBytes >> 4;
                             const uint64_t ko = static_cast<uint64_t>((kk >> 2) * kChunk16 + (kk & 3) * 2);
+                            // columns [0,32) collect dp_hi*x_hi only; both correction terms share [32,64)
                             tc::umma_tf32_ts(acc0 + b * 64, a_hi0 + b * 64 + 8 * kk, xts + ko, idesc2w, first | (kk > 0));
-                            tc::umma_tf32_ts(acc0 + b * 64, a_lo0 + b * 64 + 8 * kk, xts + ko, idesc2, true);
+                            tc::umma_tf32_ts(acc0 + b * 64 + 32, a_lo0 + b * 64 + 8 * kk, xts + ko, idesc2, true);
                         }
                     }
                 }

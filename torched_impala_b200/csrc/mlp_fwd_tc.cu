@@ -286,15 +286,20 @@ __device__ __forceinline__ void fwd_tc_body(const FwdTcArgs& a, const int cta, c
                 const uint32_t d = tmem_base + as * kAccCols;
                 const uint64_t xh = dx_hi + static_cast<uint64_t>((s * kTileBytes) >> 4);
                 const uint64_t xl = dx_lo + static_cast<uint64_t>((s * kTileBytes) >> 4);
+                // The tensor core TRUNCATES when it adds into the fp32 accumulator (measured: gradient norms
+                // ~1e-6 low, growing with the number of accumulations), so the small correction terms of all
+                // K steps are accumulated first and the hi*hi terms last: 4 full-magnitude additions, not 12.
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {  // unrolled with uniform guards: constant descriptor offsets
                     if (kk < ksteps) {
                         const uint64_t ko = 2 * kk;  // 32 bytes per K = 8 step, in 16-byte units
-                        tc::umma_tf32(d, xh + ko, dw_hi + ko, idesc, kk > 0);
-                        tc::umma_tf32(d, xl + ko, dw_hi + ko, idesc, true);
+                        tc::umma_tf32(d, xl + ko, dw_hi + ko, idesc, kk > 0);
                         tc::umma_tf32(d, xh + ko, dw_lo + ko, idesc, true);
                     }
                 }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    if (kk < ksteps) tc::umma_tf32(d, xh + 2 * kk, dw_hi + 2 * kk, idesc, true);
                 tc::umma_commit(&bars->empty[s]);      // smem stage reusable once the UMMAs retire
                 tc::umma_commit(&bars->acc_full[as]);  // accumulator ready for the epilogue
             }

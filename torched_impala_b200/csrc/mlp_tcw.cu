@@ -2,41 +2,51 @@
 // kernels of mlp_fwd_tc.cu / mlp_bwd_tc.cu do not take: observation widths up to 64 (two 128-byte
 // swizzle atoms of K) and hidden layers that are a multiple of 128 units of any size - BASELINE
 // config c5 (obs = 64, hidden = 512), where the first layer is a real GEMM (models.py:13-18,41-46 at
-// learner.py:112-113,175) and the step is bound by the tensor pipe instead of by the epilogues.
+// learner.py:112-113,175) and the step is bound by tensor-core operand traffic, not by the epilogues.
 //
 // W1' hi + lo of the WHOLE hidden layer no longer fits shared memory beside the operand stages
 // (512 x 64 x 4 B x 2 = 256 KiB), so a persistent CTA walks the hidden layer in BLOCKS of 128 units:
-// for every block it stages that block's W1 rows once (64 KiB, hi/lo, K-major SWIZZLE_128B) and then
-// streams all of its row tiles past it.  x is re-read once per block (from L2 / HBM: 4 x 212 MB at
-// c5 under ~0.5 ms of UMMA time per network), in exchange nothing is exchanged between CTAs:
+// for every block it stages that block's W1 rows once and then streams all of its row tiles past it.
+// x is re-read once per block (4 x 212 MB at c5; one thread issues cp.async.bulk.prefetch.L2 three
+// tiles ahead so the producers' register loads hit L2), in exchange nothing is exchanged between CTAs:
 //   forward   out[row] = (b2 + z_0) + z_1 + ...: the epilogue thread that owns a row adds the block's
 //             partial second-layer sum to what the SAME thread wrote in the previous pass (fixed
 //             order, bitwise reproducible, no workspace);
 //   backward  every gradient entry of W1 / b1 / W2 belongs to exactly one hidden block, so a pass
 //             produces final per-CTA partial sums for its block (dW1' accumulates in TMEM over all
 //             row tiles of the pass and is read out once per pass).
-// The bias is applied by the epilogues (an extra K atom would cost 48 KiB of shared memory; the
-// epilogues have slack here - per (tile, block) the tensor pipe needs ~2 200 cycles, the epilogue
-// ~600).  Operand split, UMMA descriptors and the transposed-DP formulation of the backward are
-// those of the narrow kernels (tc_common.cuh; mlp_bwd_tc.cu header).
+// The bias is applied by the epilogues (an extra K atom would cost 48 KiB of shared memory).
+// Operand split and UMMA descriptors are those of the narrow kernels (tc_common.cuh).
 //
-// Forward, per 128-row tile and hidden block:   D[128, 128] = X'[128, 64] * W1'_blk[128, 64]^T
+// What bounds these kernels (measured on B200, c5, ncu + CUDA events): a tf32 UMMA
+// covers only K = 8, so per instruction it moves M x 32 B of A and N x 32 B of B, and both operand
+// sources - the shared-memory descriptor fetch and tensor-memory reads (UMMA A operand AND the
+// epilogues' tcgen05.ld share that port) - deliver about 64 B/clk per SM.  Forward with both operands in
+// shared memory: 24 UMMAs x 8 KiB = 192 KiB -> 3 072 cycles per (128-row tile, block) against 1 536 of
+// math; measured 3 200 (value net) / 3 680 (policy).  Putting X' into tensor memory (TS form) was
+// measured SLOWER (3 850 / 4 960): the A reads (96 KiB) then queue behind the epilogue's 64 KiB of
+// accumulator reads on the same port.  Backward: UMMA1 with W1' in shared memory fetched 6 KiB per
+// 32 cycles of math (4 110 cycles per (64-row tile, block)); with W1' in TENSOR memory (TS, like DP for
+// UMMA2) all A operands and the epilogue share the TMEM port: 192 KiB -> 3 072, measured 3 100 / 3 730.
+//
+// Forward, per 128-row tile and hidden block:   D[128, 128] = X'[128, 64] * W1'_blk[128, 64]^T   (SS)
 //   warps 0-15  epilogue (TMEM lane = row; four warps per lane quarter take 32 hidden units each)
-//   warps 16-23 producer: coalesced 128-bit global loads of the raw x tile (next tile prefetched
-//               into registers) -> hi/lo split -> swizzled tiles, 2 stages
+//   warps 16-23 producer: coalesced 128-bit global loads of the raw x tile (next tile requested into
+//               registers before the wait for the stage) -> hi/lo split -> swizzled tiles, 2 stages
 //   warp  24    TMEM allocator + UMMA issuer (24 UMMAs M128 N128 K8 per tile at O = 64)
 // Backward, per 64-row tile and hidden block (thread owns a hidden unit, see mlp_bwd_tc.cu):
-//   UMMA1  PRE[128, 64]  = W1'_blk[128, 64] * X'[64, 64]^T                 (SS, recompute)
+//   UMMA1  PRE[128, 64]  = W1'_blk[128, 64] * X'[64, 64]^T       (TS: W1' hi / lo in TMEM, recompute)
 //   CUDA   h = relu(PRE + b1); dh = W2^T dz; dW2 += dz h; DP = PRE + b1 > 0 ? dh : 0; db1 += DP
 //   UMMA2  dW1'_blk[128, 64 | 64] += DP[128, 64] * [X'^T_hi ; X'^T_lo]    (TS: DP hi / lo from TMEM)
 //   The row-major x tile (UMMA1) and the transposed one (UMMA2) have separate full / empty
-//   barriers: the former is free again as soon as UMMA1 has retired, so the conversion of tile
-//   i + 2 does not wait for UMMA2 of tile i and two stages are enough.  DP_lo is double buffered
-//   like PRE / DP_hi (UMMAs retire in issue order: when PRE of tile i + 2 has arrived, UMMA2 of
-//   tile i is done with both).
+//   barriers: the former is free again as soon as UMMA1 has retired.  DP_lo is double buffered like
+//   PRE / DP_hi (UMMAs retire in issue order: when PRE of tile i + 2 has arrived, UMMA2 of tile i is
+//   done with both).  TMEM: [0,128) PRE / DP_hi x 2, [128,256) DP_lo x 2, [256,384) dW1', [384,512) W1'.
 //   warps 0-7 epilogue (thread = hidden unit x half of the tile's 64 rows; 13 warps leave each thread
-//   128 registers), warps 8-11 producer (thread = (row, K atom): row-major + transposed stores; dz;
-//   db2), warp 12 UMMA issuer.
+//   128 registers), warps 8-11 producer (thread = (row, K atom): row-major stores, then the transposed
+//   tile from what it has just written; dz; db2), warp 12 UMMA issuer.
+// Accumulation order: the tensor core truncates when it adds into the fp32 accumulator, so the small
+// lo*hi / hi*lo correction terms are accumulated first (or into their own columns) and hi*hi last.
 #include <cstdlib>
 
 #include "mlp_kernels.cuh"
@@ -385,13 +395,14 @@ constexpr int kBXAtomBytes = kBRows * 128;            // 8 KiB
 constexpr int kBXaBytes = 2 * kKA * kBXAtomBytes;     // row-major [hi a0][hi a1][lo a0][lo a1] = 32 KiB
 constexpr int kBXtChunkBytes = 128 * 128;             // 32 batch rows of K: rows = 64 hi features | 64 lo features
 constexpr int kBXtBytes = 2 * kBXtChunkBytes;         // 32 KiB
-constexpr int kBStages = 2;
+constexpr int kBStages = 3;
 constexpr int kBProdWarps = 4;
 constexpr int kBEpiWarps = 8;
 constexpr int kBThreads = (kBEpiWarps + kBProdWarps + 1) * 32;  // 416: 13 warps leave 128 registers per thread
 constexpr int kBIssuer = kBEpiWarps + kBProdWarps;
-constexpr int kBColLo = 128;   // TMEM columns: [0,128) PRE / DP_hi x 2, [128,256) DP_lo x 2, [256,384) dW1'
-constexpr int kBColAcc = 256;
+constexpr int kBColLo = 128;   // TMEM columns: [0,128) PRE / DP_hi x 2, [128,256) DP_lo x 2, [256,384) dW1',
+constexpr int kBColAcc = 256;  // [384,512) this pass's W1 block: 64 hi + 64 lo columns (lane = hidden unit)
+constexpr int kBColW = 384;
 
 struct BwdWArgs {
     const float* x;
@@ -413,8 +424,7 @@ template <int NP>
 __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_constant__ BwdWArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* wt = smem;                                                      // 64 KiB
-    uint8_t* xa = wt + kWBytes;                                              // kBStages x 32 KiB
+    uint8_t* xa = smem;                                                      // kBStages x 32 KiB
     uint8_t* xtb = xa + kBStages * kBXaBytes;                                // kBStages x 32 KiB
     float* dzs = reinterpret_cast<float*>(xtb + kBStages * kBXtBytes);       // [kBStages][32 row pairs][NP][2]
     float* exch = dzs + kBStages * kBRows * NP;                              // [NP + 1][128]: sums of the odd half
@@ -440,12 +450,39 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
         tc::mbar_fence_init();
     }
     if (warp == kBIssuer) tc::tmem_alloc(&bars->tmem_base, 512);
+    tc::tc_fence_before();
+    __syncthreads();  // barriers initialised, TMEM base address published
+    tc::tc_fence_after();
 
     // One pass per block of 128 hidden units, the same loop in every role (see the forward kernel);
     // the tile counter `it` keeps running across passes, so the mbarrier phases simply continue.
+    // W1' of the pass is the A operand of UMMA1 and lives in TENSOR MEMORY (TS form, like DP for UMMA2):
+    // with both operands in shared memory an M128 N64 K8 tf32 UMMA fetches 6 KiB at ~64 B/clk = 96 cycles
+    // against 32 of math.  The epilogue warps stage it (thread = hidden unit = TMEM lane, the two row
+    // halves take one K atom each): W1 row -> hi / lo -> tcgen05.st.
     auto begin_pass = [&](int hb) {
-        stage_w_block(wt, a.params + a.lay.oW1, hb, a.O, tid, kBThreads);
-        tc::fence_proxy_async();
+        if (warp < kBEpiWarps) {
+            const int q = warp & 3, atom = warp >> 2, ochunks = a.O >> 2;
+            const float* wrow = a.params + a.lay.oW1 + (size_t)(hb * kHB + 32 * q + lane) * a.O + 32 * atom;
+            const uint32_t waddr = bars->tmem_base + (static_cast<uint32_t>(32 * q) << 16) + kBColW + 32 * atom;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f), fh, fl;
+                    if (8 * atom + 4 * h + c < ochunks) w = __ldg(reinterpret_cast<const float4*>(wrow) + 4 * h + c);
+                    split4(w, fh, fl);
+                    hi[4 * c] = __float_as_uint(fh.x), hi[4 * c + 1] = __float_as_uint(fh.y);
+                    hi[4 * c + 2] = __float_as_uint(fh.z), hi[4 * c + 3] = __float_as_uint(fh.w);
+                    lo[4 * c] = __float_as_uint(fl.x), lo[4 * c + 1] = __float_as_uint(fl.y);
+                    lo[4 * c + 2] = __float_as_uint(fl.z), lo[4 * c + 3] = __float_as_uint(fl.w);
+                }
+                tc::tmem_st16(waddr + 16 * h, hi);
+                tc::tmem_st16(waddr + 64 + 16 * h, lo);
+            }
+            tc::tmem_wait_st();
+        }
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
@@ -476,11 +513,11 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             }
             const uint32_t lane_addr = bars->tmem_base + (static_cast<uint32_t>(32 * q) << 16);
             for (int i = 0; i < n_my; ++i, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1, d1 = it & 1;
+                const int s = it % kBStages, ph = (it / kBStages) & 1, d1 = it & 1, dph = (it >> 1) & 1;
                 const uint32_t c_hi = lane_addr + d1 * 64 + 32 * hh;            // PRE in, DP_hi out
                 const uint32_t c_lo = lane_addr + kBColLo + d1 * 64 + 32 * hh;  // DP_lo out
                 tc::mbar_wait(&bars->xt_full[s], ph);   // dz rows of this tile are visible
-                tc::mbar_wait(&bars->d1_full[d1], ph);  // PRE of this tile is in TMEM
+                tc::mbar_wait(&bars->d1_full[d1], dph);  // PRE of this tile is in TMEM
                 tc::tc_fence_after();
                 const float* dz_h = dzs + (s * (kBRows / 2) + 16 * hh) * 2 * NP;  // [row pair][n][2]
                 // the thread's 32 pre-activations as two halves of 16 columns: the second half is in flight
@@ -611,7 +648,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             if (pw == 0 && lane == 0) prefetch(1), prefetch(2);
             load(0);
             for (int i = 0; i < n_my; ++i, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1;
+                const int s = it % kBStages, ph = (it / kBStages) & 1;
                 if (pw == 0 && lane == 0) prefetch(i + 3);
                 // row-major tile (B of UMMA1): free once UMMA1 of the tile two back has retired
                 tc::mbar_wait(&bars->xa_empty[s], ph ^ 1);
@@ -631,7 +668,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
                 for (int n = 0; n < NP; ++n) z[n] = zn[n];
                 // the registers are free again: the next tile's rows travel while this thread waits for
                 // the transposed stage and fills it FROM THE ROW-MAJOR TILE it has just written (its own
-                // row; the stage is not rewritten before this thread does so two tiles later)
+                // row; the stage is not rewritten before this thread does so kBStages tiles later)
                 if (i + 1 < n_my) load(i + 1);
                 // transposed tile (B of UMMA2: row = feature, +64 for lo; K = this warp's 32 batch rows)
                 // and dz: free once UMMA2 of the tile two back has retired
@@ -691,36 +728,35 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
         const uint32_t idesc2w = tc::instr_desc_tf32_m128(128);    // N = 128: [hi | lo] features
         const uint32_t idesc2 = tc::instr_desc_tf32_m128(64);      // N = 64: hi features
         const int ksteps = (a.O + 7) >> 3;
-        const uint64_t dw_hi = tc::smem_desc_k_sw128(wt, 0), dw_lo = tc::smem_desc_k_sw128(wt + 2 * kWAtomBytes, 0);
         const uint64_t dxa = tc::smem_desc_k_sw128(xa, 0), dxt = tc::smem_desc_k_sw128(xtb, 0);
         int it = 0;  // tiles whose UMMA2 has been issued
         for (int hb = 0; hb < nblk; ++hb) {
             begin_pass(hb);
             const uint32_t tmem_base = bars->tmem_base;
             auto issue_umma1 = [&](int t) {  // t = running index of the tile
-                const int s = t & 1, ph = (t >> 1) & 1, d1 = t & 1;
+                const int s = t % kBStages, ph = (t / kBStages) & 1, d1 = t & 1;
                 tc::mbar_wait(&bars->xa_full[s], ph);
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint64_t xh = dxa + static_cast<uint64_t>((s * kBXaBytes) >> 4);
                     const uint64_t xl = xh + static_cast<uint64_t>((2 * kBXAtomBytes) >> 4);
                     const uint32_t d0 = tmem_base + d1 * 64;
-                    // correction terms first, hi*hi last (accumulation truncates, see the forward kernel)
+                    // A = W1' block from tensor memory (8 columns per K step), B = the x tile; correction terms
+                    // first, hi*hi last (accumulation truncates, see the forward kernel)
+                    const uint32_t w_hi = tmem_base + kBColW, w_lo = w_hi + 64;
 #pragma unroll
                     for (int kk = 0; kk < 4 * kKA; ++kk) {
                         if (kk < ksteps) {
-                            const uint64_t kw = static_cast<uint64_t>((kk >> 2) * (kWAtomBytes >> 4) + (kk & 3) * 2);
                             const uint64_t kx = static_cast<uint64_t>((kk >> 2) * (kBXAtomBytes >> 4) + (kk & 3) * 2);
-                            tc::umma_tf32(d0, dw_lo + kw, xh + kx, idesc1, kk > 0);
-                            tc::umma_tf32(d0, dw_hi + kw, xl + kx, idesc1, true);
+                            tc::umma_tf32_ts(d0, w_lo + 8 * kk, xh + kx, idesc1, kk > 0);
+                            tc::umma_tf32_ts(d0, w_hi + 8 * kk, xl + kx, idesc1, true);
                         }
                     }
 #pragma unroll
                     for (int kk = 0; kk < 4 * kKA; ++kk) {
                         if (kk < ksteps) {
-                            const uint64_t kw = static_cast<uint64_t>((kk >> 2) * (kWAtomBytes >> 4) + (kk & 3) * 2);
                             const uint64_t kx = static_cast<uint64_t>((kk >> 2) * (kBXAtomBytes >> 4) + (kk & 3) * 2);
-                            tc::umma_tf32(d0, dw_hi + kw, xh + kx, idesc1, true);
+                            tc::umma_tf32_ts(d0, w_hi + 8 * kk, xh + kx, idesc1, true);
                         }
                     }
                     tc::umma_commit(&bars->d1_full[d1]);
@@ -731,8 +767,8 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             if (n_my > 0) issue_umma1(it);
             if (n_my > 1) issue_umma1(it + 1);
             for (int i = 0; i < n_my; ++i, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1, d1 = it & 1;
-                tc::mbar_wait(&bars->dp_full[d1], ph);  // DP hi / lo of this tile are in TMEM
+                const int s = it % kBStages, ph = (it / kBStages) & 1, d1 = it & 1;
+                tc::mbar_wait(&bars->dp_full[d1], (it >> 1) & 1);  // DP hi / lo of this tile are in TMEM
                 tc::mbar_wait(&bars->xt_full[s], ph);   // its transposed x tile is in shared memory
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
@@ -762,7 +798,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
 }
 
 constexpr size_t bwd_smem_bytes(int np) {
-    return 1024 + kWBytes + kBStages * (kBXaBytes + kBXtBytes) +
+    return 1024 + kBStages * (kBXaBytes + kBXtBytes) +
            (size_t)(kBStages * kBRows * np + (np + 1) * kHB) * sizeof(float) + sizeof(BBarriers);
 }
 
