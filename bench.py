@@ -559,15 +559,19 @@ def run_own_arm(args):
     fp32_peak = SMS * FP32_LANES * 2 * pk["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at max SM clock
     tf32_peak = pk["bf16_tflops"] / 2.0  # tf32 UMMA rate = half the (measured) bf16 rate
     H, O, A = eng.H_pi, eng.O, eng.A
-    on_tc = (os.environ.get("IMPALA_MLP_TC", "1") != "0" and O % 4 == 0 and 4 <= O <= 28
-             and H in (128, 256) and A <= 4)
-    # tensor-core work actually issued: 3xTF32 (3 UMMAs per product); forward K = [x | 1] padded to
-    # a multiple of 8; the backward runs two GEMMs per row: the recompute (K = O padded to 8, bias
-    # added on the CUDA cores) and the dW1 reduction (32 output columns)
-    kf, kb = (O + 1 + 7) // 8 * 8, (O + 7) // 8 * 8
+    tc_on = os.environ.get("IMPALA_MLP_TC", "1") != "0" and O % 4 == 0 and A <= 4
+    narrow = tc_on and 4 <= O <= 28 and H in (128, 256)                       # mlp_fwd_tc.cu / mlp_bwd_tc.cu
+    wide = (tc_on and not narrow and 4 <= O <= 64 and H % 128 == 0 and H <= 4096
+            and os.environ.get("IMPALA_MLP_TCW", "1") != "0")                 # mlp_tcw.cu (c5)
+    on_tc = narrow or wide
+    # tensor-core work actually issued: 3xTF32 (3 UMMAs per product).  Narrow kernels: forward and recompute
+    # K = [x | 1] padded to a multiple of 8, dW1 reduction over 32 output columns.  Wide kernels: K = O
+    # padded to 8 (the bias is added on the CUDA cores), dW1 reduction over 64 output columns.
+    kb = (O + 7) // 8 * 8
+    kf, ncol = ((O + 1 + 7) // 8 * 8, 32) if narrow else (kb, 64)
     executed = {"mlp_forward(policy)": 2.0 * eng.M_pi * H * kf * 3, "mlp_forward(value_fn)": 2.0 * eng.M_vf * H * kf * 3,
-                "mlp_backward(policy)": 2.0 * eng.M_pi * H * (kb + 32) * 3,
-                "mlp_backward(value_fn)": 2.0 * eng.M_vf * H * (kb + 32) * 3}
+                "mlp_backward(policy)": 2.0 * eng.M_pi * H * (kf + ncol) * 3,
+                "mlp_backward(value_fn)": 2.0 * eng.M_vf * H * (kf + ncol) * 3}
     executed["mlp_forward_pair(policy+value_fn)"] = executed["mlp_forward(policy)"] + executed["mlp_forward(value_fn)"]
     executed["mlp_backward_pair(policy+value_fn)"] = executed["mlp_backward(policy)"] + executed["mlp_backward(value_fn)"]
     kernels = {}
@@ -594,7 +598,9 @@ def run_own_arm(args):
         kernels[n]["in_step"] = n in in_step
     dom = max(in_step, key=lambda n: kernels[n]["us"])
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    # ncu dram__bytes per launch of the dominant kernel: profiles/dram_traffic.json is the c4 capture,
+    # other configs have their own file (dram_traffic_c5.json) or report null
+    prof = os.path.join(ROOT, "profiles", "dram_traffic.json" if args.config == "c4" else f"dram_traffic_{args.config}.json")
     if os.path.exists(prof):
         with open(prof) as f:
             traffic = json.load(f).get(dom)

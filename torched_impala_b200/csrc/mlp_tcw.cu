@@ -23,9 +23,11 @@
 // sources - the shared-memory descriptor fetch and tensor-memory reads (UMMA A operand AND the
 // epilogues' tcgen05.ld share that port) - deliver about 64 B/clk per SM.  Forward with both operands in
 // shared memory: 24 UMMAs x 8 KiB = 192 KiB -> 3 072 cycles per (128-row tile, block) against 1 536 of
-// math; measured 3 200 (value net) / 3 680 (policy).  Putting X' into tensor memory (TS form) was
-// measured SLOWER (3 850 / 4 960): the A reads (96 KiB) then queue behind the epilogue's 64 KiB of
-// accumulator reads on the same port.  Backward: UMMA1 with W1' in shared memory fetched 6 KiB per
+// math; measured 3 200 (value net) / 3 680 (policy).  Putting X' into tensor memory (TS form, producer
+// thread = row writing tcgen05.st) was measured SLOWER (3 850 / 4 960 cycles), and so was the split
+// "x_hi from tensor memory, x_lo from shared memory" that halves the traffic of either port
+// (4 250 / 4 950): in the forward the A reads queue behind the epilogue's 64 KiB of accumulator reads
+// per tile on the same port, and the row-per-thread producer loses the coalesced loads.  Backward: UMMA1 with W1' in shared memory fetched 6 KiB per
 // 32 cycles of math (4 110 cycles per (64-row tile, block)); with W1' in TENSOR memory (TS, like DP for
 // UMMA2) all A operands and the epilogue share the TMEM port: 192 KiB -> 3 072, measured 3 100 / 3 730.
 //
