@@ -4,7 +4,7 @@
 
 Mnemonics that prove the Blackwell-native paths (B200_PROFILING.md): UTC*MMA = tcgen05.mma,
 LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA bulk copy),
-SYNCS = mbarrier, FFMA2 / FADD2 / FMUL2 = packed fp32, ACQBULK / CCTL etc. as they appear."""
+SYNCS = mbarrier, FFMA2 / FADD2 / FMUL2 = packed fp32, UBLKPF = cp.async.bulk.prefetch.L2, ACQBULK / CCTL etc. as they appear."""
 import collections
 import os
 import re
@@ -16,7 +16,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "torched_impala_b
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "MUFU",
        "LDG.E.128", "STG.E.128", "LDGSTS", "HMMA", "DADD", "DFMA", "SHFL", "BAR.SYNC", "ATOM", "RED", "MEMBAR", "LDS", "STS",
-       "ELECT", "ACQBULK", "ERRBAR", "NANOSLEEP")
+       "ELECT", "ACQBULK", "ERRBAR", "NANOSLEEP", "UBLKPF")
 cur, hist, total, order = None, collections.defaultdict(collections.Counter), collections.Counter(), []
 for ln in sass.splitlines():
     m = re.search(r"Function : (\S+)", ln)
