@@ -30,6 +30,7 @@
 // per tile on the same port, and the row-per-thread producer loses the coalesced loads.  Backward: UMMA1 with W1' in shared memory fetched 6 KiB per
 // 32 cycles of math (4 110 cycles per (64-row tile, block)); with W1' in TENSOR memory (TS, like DP for
 // UMMA2) all A operands and the epilogue share the TMEM port: 192 KiB -> 3 072, measured 3 100 / 3 730.
+// (Taking W1'_lo from shared memory again for the lo*hi product - 160 / 128 KiB - with two x stages: 3 330 / 3 850.)
 //
 // Forward, per 128-row tile and hidden block:   D[128, 128] = X'[128, 64] * W1'_blk[128, 64]^T   (SS)
 //   warps 0-15  epilogue (TMEM lane = row; four warps per lane quarter take 32 hidden units each)
