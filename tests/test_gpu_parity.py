@@ -54,6 +54,7 @@ MLP_SHAPES = [
     (97, 32, 128, 16), (64, 8, 100, 5), (4097, 24, 256, 4), (86016, 24, 256, 1), (700, 28, 96, 3),
     # wide tensor-core kernels (mlp_tcw.cu): O <= 64, H a multiple of 128, several tiles and passes per CTA
     (60001, 64, 512, 4), (60001, 64, 512, 1), (1000, 40, 384, 3), (130, 24, 512, 1), (257, 32, 128, 2),
+    (5, 64, 512, 4), (129, 4, 512, 2),
 ]
 
 

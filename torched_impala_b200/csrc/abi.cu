@@ -100,3 +100,7 @@ extern "C" int impala_peer_free(void* dev_ptr) {
     cudaError_t e = cudaFree(dev_ptr);
     return e == cudaSuccess ? IMPALA_OK : (int)e;
 }
+
+// Debug only (not part of the public ABI): the pending error of this library's (statically linked)
+// runtime instance, cleared by the call.
+extern "C" int impala_debug_last_error(void) { return (int)cudaGetLastError(); }

@@ -29,6 +29,11 @@ struct GridInfo {
 };
 std::mutex g_cfg_mutex;
 std::map<std::tuple<const void*, int, int, size_t>, GridInfo> g_cfg_cache;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the KERNEL (per device), not of one launch
+// configuration: it is only ever raised.  (Setting it per (threads, smem) entry lowered it when the same
+// instantiation was used with a narrower hidden layer, and the next launch of the wider, already
+// cached configuration failed with cudaErrorInvalidValue.)
+std::map<std::pair<const void*, int>, size_t> g_smem_opt_in;
 
 // grad[i] = sum_c ws[c][i] in float64.  A CTA covers 32 consecutive entries (one 128-byte
 // line per partial row); its 8 warps split the partial rows, so every load instruction is
@@ -128,8 +133,12 @@ int impala_mlp_launch(void (*kernel)(MlpArgs), const MlpArgs& a, const MlpConfig
         const auto key = std::make_tuple((const void*)kernel, dev, c.threads, smem);
         auto it = g_cfg_cache.find(key);
         if (it == g_cfg_cache.end()) {
-            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
+            size_t& opted = g_smem_opt_in[std::make_pair((const void*)kernel, dev)];
+            if (smem > opted) {
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                opted = smem;
+            }
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gi.ctas_per_sm, kernel, c.threads, smem);
             if (e != cudaSuccess) return (int)e;
             e = cudaDeviceGetAttribute(&gi.sms, cudaDevAttrMultiProcessorCount, dev);
