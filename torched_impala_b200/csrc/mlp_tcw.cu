@@ -100,18 +100,29 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 }
 
 // Rows [128 hb, 128 hb + 128) of W1 (H, O) -> hi / lo K-major SWIZZLE_128B tiles (columns >= O zero).
-__device__ __forceinline__ void stage_w_block(uint8_t* wt, const float* __restrict__ W1, int hb, int O, int tid,
-                                              int nthreads) {
+// All global loads of a thread are issued before the first conversion (the rows are L2-resident
+// parameters; a load -> convert -> store loop would serialise its round trips at every pass).
+template <int NTHREADS>
+__device__ __forceinline__ void stage_w_block(uint8_t* wt, const float* __restrict__ W1, int hb, int O, int tid) {
+    constexpr int kIt = (kHB * 16 + NTHREADS - 1) / NTHREADS;
     const int ochunks = O >> 2;
-    for (int idx = tid; idx < kHB * 16; idx += nthreads) {
-        const int r = idx >> 4, c = idx & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ochunks) v = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)(hb * kHB + r) * O) + c);
-        float4 hi, lo;
-        split4(v, hi, lo);
-        const uint32_t off = (c >> 3) * kWAtomBytes + tc::sw128_offset(r, c & 7);
-        *reinterpret_cast<float4*>(wt + off) = hi;
-        *reinterpret_cast<float4*>(wt + 2 * kWAtomBytes + off) = lo;
+    float4 v[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = tid + it * NTHREADS, r = idx >> 4, c = idx & 15;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < kHB * 16 && c < ochunks) v[it] = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)(hb * kHB + r) * O) + c);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = tid + it * NTHREADS, r = idx >> 4, c = idx & 15;
+        if (idx < kHB * 16) {
+            float4 hi, lo;
+            split4(v[it], hi, lo);
+            const uint32_t off = (c >> 3) * kWAtomBytes + tc::sw128_offset(r, c & 7);
+            *reinterpret_cast<float4*>(wt + off) = hi;
+            *reinterpret_cast<float4*>(wt + 2 * kWAtomBytes + off) = lo;
+        }
     }
 }
 
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
     // pass by then, so every UMMA has retired.  The tile counter `it` keeps running across passes,
     // so the mbarrier phases simply continue.
     auto begin_pass = [&](int hb) {
-        stage_w_block(wt, a.params + a.lay.oW1, hb, a.O, tid, kFThreads);
+        stage_w_block<kFThreads>(wt, a.params + a.lay.oW1, hb, a.O, tid);
         const float* __restrict__ W2 = a.params + a.lay.oW2;
         const float* __restrict__ b1 = a.params + a.lay.ob1;
         for (int idx = tid; idx < kHB * NP; idx += kFThreads) {
@@ -303,16 +314,18 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
                 if (row < a.M && c < ochunks) v[k] = ldg_v4(a.x + (size_t)row * a.O + 4 * c);
             }
         };
+        auto prefetch = [&](int i) {  // one thread: the tile's rows are contiguous
+            const int64_t row0 = (int64_t)(cta + i * ncta) * kFTileM;
+            const int64_t rows = a.M - row0 < kFTileM ? a.M - row0 : kFTileM;
+            if (i < n_my && rows > 0) prefetch_l2(a.x + row0 * a.O, (uint32_t)(rows * a.O * 4));
+        };
         int it = 0;
         for (int hb = 0; hb < nblk; ++hb) {
             begin_pass(hb);
-            auto prefetch = [&](int i) {  // one thread: the tile's rows are contiguous
-                const int64_t row0 = (int64_t)(cta + i * ncta) * kFTileM;
-                const int64_t rows = a.M - row0 < kFTileM ? a.M - row0 : kFTileM;
-                if (i < n_my && rows > 0) prefetch_l2(a.x + row0 * a.O, (uint32_t)(rows * a.O * 4));
-            };
-            if (ptid == 0) prefetch(1), prefetch(2);
-            if (n_my > 0) load(0);
+            if (hb == 0) {  // later passes: requested before the previous pass's closing barrier (below)
+                if (ptid == 0) prefetch(1), prefetch(2);
+                load(0);
+            }
             for (int i = 0; i < n_my; ++i, ++it) {
                 const int s = it % kFStages, ph = (it / kFStages) & 1;
                 if (ptid == 0) prefetch(i + 3);
@@ -331,6 +344,10 @@ __global__ void __launch_bounds__(kFThreads, 1) mlp_fwd_tcw_kernel(const __grid_
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&bars->full[s]);
                 if (i + 1 < n_my) load(i + 1);  // in flight while this thread waits for the next stage
+            }
+            if (hb + 1 < nblk) {  // the next pass starts with the same tiles: its first rows travel during the
+                if (ptid == 0) prefetch(1), prefetch(2);  // drain of this pass and the staging of the next block
+                load(0);
             }
             end_pass();
         }
@@ -648,8 +665,10 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
             float gb2[NP];
 #pragma unroll
             for (int n = 0; n < NP; ++n) gb2[n] = 0.f;
-            if (pw == 0 && lane == 0) prefetch(1), prefetch(2);
-            load(0);
+            if (hb == 0) {  // later passes: requested before the previous pass's closing barrier (below)
+                if (pw == 0 && lane == 0) prefetch(1), prefetch(2);
+                load(0);
+            }
             for (int i = 0; i < n_my; ++i, ++it) {
                 const int s = it % kBStages, ph = (it / kBStages) & 1;
                 if (pw == 0 && lane == 0) prefetch(i + 3);
@@ -702,6 +721,10 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_bwd_tcw_kernel(const __grid_
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(&bars->xt_full[s]);
+            }
+            if (hb + 1 < nblk) {  // the next pass starts with the same tiles: its first rows travel during the
+                if (pw == 0 && lane == 0) prefetch(1), prefetch(2);  // read-out of this pass and the staging of the next block
+                load(0);
             }
             if (hb == 0) {  // db2 = column sums of dout over this CTA's rows: fixed-order tree over 64 threads
 #pragma unroll
