@@ -81,7 +81,8 @@ __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) 
 }
 // The same split for the streamed operand in 3 instead of 5 SASS instructions per element (the
 // producers share issue slots with the epilogue): hi = x rounded to tf32, half away from zero (add half
-// a tf32 ulp to the magnitude bits, clear the low 13), lo = x - hi exactly.
+// a tf32 ulp to the magnitude bits, clear the low 13), lo = x - hi exactly.  (|x| within 2^-11 of FLT_MAX
+// rounds up to inf like any round-to-nearest conversion would; observations are nowhere near.)
 __device__ __forceinline__ void split_fast(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
