@@ -121,6 +121,10 @@ class _Publisher:
         self.free = [threading.Event(), threading.Event()]
         for e in self.free:
             e.set()
+        # CUDA events of a slot are reused: a slot is posted again only after its previous publication
+        # has been written (free[s] set after landed.synchronize())
+        self.ev_frozen = [torch.cuda.Event() for _ in range(2)]
+        self.ev_landed = [torch.cuda.Event() for _ in range(2)]
         self.views = []  # (flat offset, shared tensor) of the policy's four parameters
         sd = policy.state_dict()
         for grp, key, off, shp in eng._segments():
@@ -146,14 +150,13 @@ class _Publisher:
         self.i += 1
         self.free[s].clear()
         eng = self.eng
-        with torch.cuda.stream(eng.stream):
+        frozen, landed = self.ev_frozen[s], self.ev_landed[s]
+        with eng._on_stream():
             self.stage[s].copy_(eng.params[:eng.n_pi], non_blocking=True)
-            frozen = torch.cuda.Event()
             frozen.record(eng.stream)
         self.stream.wait_event(frozen)
         with torch.cuda.stream(self.stream):
             self.host[s].copy_(self.stage[s], non_blocking=True)
-            landed = torch.cuda.Event()
             landed.record(self.stream)
         self.q.put((s, n, landed))
         return True
@@ -439,6 +442,7 @@ class Learner:
             if leader is not None:
                 leader.wait_ready()
             done, slot, pending, stage_k = 0, 0, None, 0
+            eng.loop_stream(True)  # this thread's current stream is the engine's for the whole loop
             # IMPALA_LOOP_STATS=1: where the host time of the update loop goes (printed at the end)
             stats = {"release_wait": 0.0, "collect": 0.0, "enqueue": 0.0, "post": 0.0, "finish": 0.0} \
                 if os.environ.get("IMPALA_LOOP_STATS") else None
