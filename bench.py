@@ -191,13 +191,14 @@ def learner_e2e(config: str, devices: int):
     32 synthetic actor processes (scripts/learner_e2e.py, fresh interpreter - this process has CUDA
     initialised and must not fork a CUDA child).  Includes queue -> slab packing in the actors, the
     per-rank shard DMAs, the update and the weight publication."""
-    if config not in ("c3", "c4"):
+    if config not in ("c3", "c4", "c5"):
         return None
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
+    updates, warm = ("600", "100") if config != "c5" else ("200", "30")  # c5: 212 MB per update over PCIe
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "learner_e2e.py"), "--config", config, "--actors", "32",
-           "--updates", "600", "--warmup", "100", "--devices", str(devices), "--deadline", "90"]
+           "--updates", updates, "--warmup", warm, "--devices", str(devices), "--deadline", "90"]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
         for ln in reversed(res.stdout.splitlines()):

@@ -29,7 +29,7 @@ from torched_impala_b200.ring import RingQueue  # noqa: E402
 from torched_impala_b200.utils import Counter, default_hparams  # noqa: E402
 
 CFG = {"c3": dict(T=20, B=1024, O=24, A=4, H=256), "c4": dict(T=20, B=4096, O=24, A=4, H=256),
-       "c1": dict(T=20, B=8, O=4, A=2, H=32)}
+       "c1": dict(T=20, B=8, O=4, A=2, H=32), "c5": dict(T=100, B=8192, O=64, A=4, H=512)}
 
 
 def actor_main(aid, ring, learner_done, w, payload, block, seed):
